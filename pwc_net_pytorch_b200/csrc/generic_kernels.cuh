@@ -1,0 +1,229 @@
+// Generic (any pad/kernel/displacement/stride) correlation kernels and the standalone warp.
+// These cover the parts of the reference operator's parameter space that the tiled fast paths
+// do not (kernel_size > 1, stride1 > 1, pad != max_displacement).  One thread per result
+// element, direct NCHW addressing: no padded channels-last scratch copy
+// (correlation_cuda_kernel.cu:10-32 and the fills of correlation_cuda.c:36-42 are not needed).
+#pragma once
+#include "pwc_common.cuh"
+
+namespace pwc {
+
+struct CorrGeom {
+    int B, C, H, W;
+    int pad, k, md, s1, s2;
+    int kr, r, D, oc, oh, ow;
+};
+
+// value of the zero-padded second operand at padded coordinates (yp, xp); warped on the fly
+// when flow != nullptr (the pixel's own flow decides where f2 is sampled, model.py:80).
+__device__ __forceinline__ float second_operand(const float* __restrict__ f2n,
+                                                const float* __restrict__ flown, int c, int yp,
+                                                int xp, const CorrGeom& g)
+{
+    const int y = yp - g.pad, x = xp - g.pad;
+    if (y < 0 || y >= g.H || x < 0 || x >= g.W) return 0.0f;
+    const size_t HW = (size_t)g.H * g.W;
+    const float* plane = f2n + (size_t)c * HW;
+    if (flown == nullptr) return __ldg(plane + (size_t)y * g.W + x);
+    const float u = __ldg(flown + (size_t)y * g.W + x);
+    const float v = __ldg(flown + HW + (size_t)y * g.W + x);
+    const Tap t = make_tap((float)x + u, (float)y + v, g.H, g.W);
+    return t.off < 0 ? 0.0f : tap_sample(t, plane);
+}
+
+__device__ __forceinline__ float first_operand(const float* __restrict__ f1n, int c, int yp,
+                                               int xp, const CorrGeom& g)
+{
+    const int y = yp - g.pad, x = xp - g.pad;
+    if (y < 0 || y >= g.H || x < 0 || x >= g.W) return 0.0f;
+    return __ldg(f1n + ((size_t)c * g.H + y) * g.W + x);
+}
+
+// correlation_cuda_kernel.cu:45-101 for arbitrary parameters, optionally fused with the warp
+// and the activation.
+__global__ void __launch_bounds__(256)
+corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                        const float* __restrict__ flow, float* __restrict__ out, CorrGeom g,
+                        int act, float slope)
+{
+    const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int bx = (int)(idx % g.ow);
+    const int by = (int)((idx / g.ow) % g.oh);
+    const int tc = (int)((idx / ((size_t)g.ow * g.oh)) % g.oc);
+    const int n = (int)(idx / ((size_t)g.ow * g.oh * g.oc));
+    const int ti = tc % g.D - g.r, tj = tc / g.D - g.r;
+    const int y1 = by * g.s1 + g.md + g.kr, x1 = bx * g.s1 + g.md + g.kr;
+    const int y2 = y1 + tj * g.s2, x2 = x1 + ti * g.s2;
+    const size_t HW = (size_t)g.H * g.W;
+    const float* f1n = f1 + (size_t)n * g.C * HW;
+    const float* f2n = f2 + (size_t)n * g.C * HW;
+    const float* flown = flow ? flow + (size_t)n * 2 * HW : nullptr;
+    float s = 0.0f;
+    for (int j = -g.kr; j <= g.kr; ++j)
+        for (int i = -g.kr; i <= g.kr; ++i)
+            for (int c = 0; c < g.C; ++c)
+                s = fmaf(first_operand(f1n, c, y1 + j, x1 + i, g),
+                         second_operand(f2n, flown, c, y2 + j, x2 + i, g), s);
+    float v = s / (float)(g.k * g.k * g.C);
+    if (act) v = leaky(v, slope);
+    out[idx] = v;
+}
+
+// correlation_cuda_kernel.cu:119-196 (gradInput1) and :211-288 (gradInput2) for stride1 == 1,
+// arbitrary pad / kernel_size / displacement / stride2; same window arithmetic as the reference
+// (C truncating division).  One thread per (n, c, y, x); both gradients in one pass.
+// `second` is the (already warped) second operand.  gate != nullptr applies leaky_relu_'s
+// derivative by the sign of the forward output.
+__global__ void __launch_bounds__(256)
+corr_bwd_generic_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
+                        const float* __restrict__ f1, const float* __restrict__ second,
+                        float* __restrict__ g1, float* __restrict__ g2, CorrGeom g, float slope)
+{
+    const size_t total = (size_t)g.B * g.C * g.H * g.W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int xx = (int)(idx % g.W);
+    const int yy = (int)((idx / g.W) % g.H);
+    const int c = (int)((idx / ((size_t)g.W * g.H)) % g.C);
+    const int n = (int)(idx / ((size_t)g.W * g.H * g.C));
+    const size_t HW = (size_t)g.H * g.W;
+    const float* f1n = f1 + (size_t)n * g.C * HW;
+    const float* f2n = second + (size_t)n * g.C * HW;
+    const size_t ohw = (size_t)g.oh * g.ow;
+    const float* gon = gout + (size_t)n * g.oc * ohw;
+    const float* gaten = gate ? gate + (size_t)n * g.oc * ohw : nullptr;
+    const int y = yy * g.s1 + g.pad, x = xx * g.s1 + g.pad;
+    const float nelems = (float)(g.k * g.k * g.C);
+
+    float a1 = 0.0f, a2 = 0.0f;
+    for (int tc = 0; tc < g.oc; ++tc) {
+        const int i2 = (tc % g.D - g.r) * g.s2, j2 = (tc / g.D - g.r) * g.s2;
+        // ---- input1 window (:129-149): independent of tc ----
+        {
+            int xmin = (x - g.kr - g.md) / g.s1, ymin = (y - g.kr - g.md) / g.s1;
+            int xmax = (x + g.kr - g.md) / g.s1, ymax = (y + g.kr - g.md) / g.s1;
+            const bool skip = (xmax < 0 || ymax < 0 || xmin >= g.ow || ymin >= g.oh) ||
+                              (xmin > xmax || ymin > ymax);
+            if (!skip) {
+                xmin = max(0, xmin); xmax = min(g.ow - 1, xmax);
+                ymin = max(0, ymin); ymax = min(g.oh - 1, ymax);
+                const float v2 = second_operand(f2n, nullptr, c, y + j2, x + i2, g);
+                float s = 0.0f;
+                for (int j = ymin; j <= ymax; ++j)
+                    for (int i = xmin; i <= xmax; ++i) {
+                        const size_t o = (size_t)tc * ohw + (size_t)j * g.ow + i;
+                        float gv = __ldg(gon + o);
+                        if (gaten && __ldg(gaten + o) < 0.0f) gv *= slope;
+                        s += gv;
+                    }
+                a1 = fmaf(s, v2, a1);
+            }
+        }
+        // ---- input2 window (:246-266) ----
+        {
+            int xmin = (x - g.kr - g.md - i2) / g.s1, ymin = (y - g.kr - g.md - j2) / g.s1;
+            int xmax = (x + g.kr - g.md - i2) / g.s1, ymax = (y + g.kr - g.md - j2) / g.s1;
+            const bool skip = (xmax < 0 || ymax < 0 || xmin >= g.ow || ymin >= g.oh) ||
+                              (xmin > xmax || ymin > ymax);
+            if (!skip) {
+                xmin = max(0, xmin); xmax = min(g.ow - 1, xmax);
+                ymin = max(0, ymin); ymax = min(g.oh - 1, ymax);
+                const float v1 = first_operand(f1n, c, y - j2, x - i2, g);
+                float s = 0.0f;
+                for (int j = ymin; j <= ymax; ++j)
+                    for (int i = xmin; i <= xmax; ++i) {
+                        const size_t o = (size_t)tc * ohw + (size_t)j * g.ow + i;
+                        float gv = __ldg(gon + o);
+                        if (gaten && __ldg(gaten + o) < 0.0f) gv *= slope;
+                        s += gv;
+                    }
+                a2 = fmaf(s, v1, a2);
+            }
+        }
+    }
+    g1[idx] = a1 / nelems;
+    g2[idx] = a2 / nelems;
+}
+
+// WarpingLayer.forward (modules.py:31-42): one thread per (n, channel group, y, x).
+template <int CPT>
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
+                float* __restrict__ out, int B, int C, int H, int W)
+{
+    const int cgroups = cdiv(C, CPT);
+    const size_t HW = (size_t)H * W;
+    const size_t total = (size_t)B * cgroups * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t pix = idx % HW;
+    const int cg = (int)((idx / HW) % cgroups);
+    const int n = (int)(idx / (HW * cgroups));
+    const int yy = (int)(pix / W), xx = (int)(pix % W);
+    const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
+    const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
+    const Tap t = make_tap((float)xx + u, (float)yy + v, H, W);
+    const int c0 = cg * CPT;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int c = c0 + k;
+        if (c < C) {
+            const size_t plane = ((size_t)n * C + c) * HW;
+            out[plane + pix] = t.off < 0 ? 0.0f : tap_sample(t, x + plane);
+        }
+    }
+}
+
+// Autograd of WarpingLayer.  grad_x must be zeroed beforehand
+// (the ABI entry does it on the same stream).  One thread per (n, y, x): the flow gradient is a
+// plain sum over channels (deterministic), the feature gradient a scatter-add.
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
+                const float* __restrict__ flow, float* __restrict__ gx,
+                float* __restrict__ gflow, int B, int C, int H, int W)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t total = (size_t)B * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t pix = idx % HW;
+    const int n = (int)(idx / HW);
+    const int yy = (int)(pix / W), xx = (int)(pix % W);
+    const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
+    const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
+    const float sx = (float)xx + u, sy = (float)yy + v;
+    const Tap t = make_tap(sx, sy, H, W);
+    float gu = 0.0f, gv = 0.0f;
+    if (t.off >= 0) {
+        const float ax = sx - floorf(sx), ay = sy - floorf(sy);
+        // corners outside the image read as 0 (their clamped addresses are masked out)
+        const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+        const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
+        const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
+        const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const size_t plane = ((size_t)n * C + c) * HW;
+            const float g = __ldg(gout + plane + pix);
+            const float* p = x + plane + t.off;
+            const float v00 = m00 * __ldg(p), v01 = m01 * __ldg(p + t.dx);
+            const float v10 = m10 * __ldg(p + t.dyw), v11 = m11 * __ldg(p + t.dyw + t.dx);
+            gu = fmaf(g, fmaf(v11 - v10, ay, (v01 - v00) * (1.0f - ay)), gu);
+            gv = fmaf(g, fmaf(v11 - v01, ax, (v10 - v00) * (1.0f - ax)), gv);
+            if (gx) {
+                float* q = gx + plane + t.off;
+                if (t.w00 != 0.0f) atomicAdd(q, g * t.w00);
+                if (t.w01 != 0.0f) atomicAdd(q + t.dx, g * t.w01);
+                if (t.w10 != 0.0f) atomicAdd(q + t.dyw, g * t.w10);
+                if (t.w11 != 0.0f) atomicAdd(q + t.dyw + t.dx, g * t.w11);
+            }
+        }
+    }
+    if (gflow) {
+        gflow[(size_t)n * 2 * HW + pix] = gu;
+        gflow[(size_t)n * 2 * HW + HW + pix] = gv;
+    }
+}
+
+}  // namespace pwc

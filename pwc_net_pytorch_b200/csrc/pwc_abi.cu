@@ -1,0 +1,283 @@
+// extern "C" surface of libpwc_b200.so (declared in include/pwc_b200.h) and kernel dispatch.
+// Plain pointers and sizes only; no torch types.  Never allocates, frees or synchronises.
+#include "../../include/pwc_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "corr_bwd.cuh"
+#include "generic_kernels.cuh"
+#include "pwc_common.cuh"
+#include "warpcorr_fwd.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_force_generic{0};
+
+int fail(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 0;
+}
+
+int check_launch(const char* what)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+
+bool make_geom(pwc::CorrGeom& g, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("non-positive tensor size") != 0;
+    if (pad < 0 || k < 1 || (k & 1) == 0 || md < 0 || s1 < 1 || s2 < 1)
+        return fail("bad correlation parameters (pad=%d k=%d md=%d s1=%d s2=%d); kernel_size must "
+                    "be odd and >= 1, strides >= 1", pad, k, md, s1, s2) != 0;
+    g.B = B; g.C = C; g.H = H; g.W = W;
+    g.pad = pad; g.k = k; g.md = md; g.s1 = s1; g.s2 = s2;
+    g.kr = (k - 1) / 2;
+    g.r = md / s2;
+    g.D = 2 * g.r + 1;
+    g.oc = g.D * g.D;
+    // ceil((padded - 2*border) / stride1), correlation_cuda.c:25-34
+    const int nh = H + 2 * pad - 2 * (g.kr + md), nw = W + 2 * pad - 2 * (g.kr + md);
+    g.oh = nh > 0 ? (nh + s1 - 1) / s1 : 0;
+    g.ow = nw > 0 ? (nw + s1 - 1) / s1 : 0;
+    if (g.oh <= 0 || g.ow <= 0) return fail("empty correlation output (%d x %d)", g.oh, g.ow) != 0;
+    if ((size_t)B * g.oc * g.oh * g.ow >= ((size_t)1 << 40)) return fail("output too large") != 0;
+    return true;
+}
+
+bool fast_path(const pwc::CorrGeom& g)
+{
+    return !g_force_generic.load() && g.k == 1 && g.s1 == 1 && g.pad == g.md && g.D == 9 &&
+           (g.s2 == 1 || g.s2 == 2);
+}
+
+template <class Cfg, bool HAS_FLOW>
+int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
+                     float* warped, const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+{
+    auto kern = pwc::warpcorr_fwd_kernel<Cfg, HAS_FLOW>;
+    const size_t smem = Cfg::smem_bytes(HAS_FLOW);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+        configured_dev = dev;
+    }
+    const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
+    const long long blocks = (long long)tiles_x * tiles_y * g.B;
+    if (blocks > 0x7fffffffLL) return fail("grid too large");
+    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(f1, f2, flow, out, warped, g.C, g.H, g.W, tiles_x,
+                                                  tiles_y, act, slope);
+    return check_launch("warpcorr_fwd_kernel");
+}
+
+template <int S2, bool HAS_FLOW>
+int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
+                       float* warped, const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+{
+    if (g.W > 16)
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
+    return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
+}
+
+int forward_impl(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+                 const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+{
+    if (fast_path(g)) {
+        if (g.s2 == 1)
+            return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, out, warped, g, act, slope, st)
+                        : dispatch_fwd_tiled<1, false>(f1, f2, flow, out, warped, g, act, slope, st);
+        return flow ? dispatch_fwd_tiled<2, true>(f1, f2, flow, out, warped, g, act, slope, st)
+                    : dispatch_fwd_tiled<2, false>(f1, f2, flow, out, warped, g, act, slope, st);
+    }
+    const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
+    pwc::corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f1, f2, flow, out, g, act, slope);
+    if (!check_launch("corr_fwd_generic_kernel")) return 0;
+    if (warped) {
+        if (flow) return pwc_warp_forward(f2, flow, warped, g.B, g.C, g.H, g.W, st);
+        if (cudaMemcpyAsync(warped, f2, sizeof(float) * (size_t)g.B * g.C * g.H * g.W,
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return fail("cudaMemcpyAsync(warped_out): %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return 1;
+}
+
+template <int S2, int SIGN>
+int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float* res,
+                     const pwc::CorrGeom& g, float slope, cudaStream_t st)
+{
+    using Cfg = pwc::BwdCfg<9, S2, 16>;
+    auto kern = pwc::corr_bwd_kernel<Cfg, SIGN>;
+    const size_t smem = Cfg::smem_bytes();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+        configured_dev = dev;
+    }
+    const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
+    const long long blocks = (long long)tiles_x * tiles_y * g.B;
+    if (blocks > 0x7fffffffLL) return fail("grid too large");
+    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, slope);
+    return check_launch("corr_bwd_kernel");
+}
+
+// g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
+int corr_backward_impl(const float* gout, const float* gate, const float* f1, const float* second,
+                       float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st)
+{
+    if (g.s1 != 1)
+        return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
+                    "address gradInput out of range otherwise", g.s1);
+    if (fast_path(g)) {
+        if (g.s2 == 1)
+            return launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, st) &&
+                   launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, st);
+        return launch_bwd_tiled<2, +1>(gout, gate, second, g1, g, slope, st) &&
+               launch_bwd_tiled<2, -1>(gout, gate, f1, g2, g, slope, st);
+    }
+    const size_t total = (size_t)g.B * g.C * g.H * g.W;
+    pwc::corr_bwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gout, gate, f1, second, g1, g2, g, slope);
+    return check_launch("corr_bwd_generic_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pwc_last_error(void) { return g_err; }
+int pwc_abi_version(void) { return PWC_B200_ABI_VERSION; }
+long long pwc_launch_count(void) { return g_launches.load(); }
+int pwc_set_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
+
+int pwc_corr_output_shape(int H, int W, int pad_size, int kernel_size, int max_displacement,
+                          int stride1, int stride2, int* out_channels, int* out_h, int* out_w)
+{
+    pwc::CorrGeom g;
+    if (!make_geom(g, 1, 1, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    if (out_channels) *out_channels = g.oc;
+    if (out_h) *out_h = g.oh;
+    if (out_w) *out_w = g.ow;
+    return 1;
+}
+
+int pwc_warp_forward(const float* x, const float* flow, float* out, int B, int C, int H, int W,
+                     cudaStream_t stream)
+{
+    if (!x || !flow || !out) return fail("pwc_warp_forward: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("pwc_warp_forward: non-positive size");
+    constexpr int CPT = 4;
+    const size_t total = (size_t)B * pwc::cdiv(C, CPT) * H * W;
+    pwc::warp_fwd_kernel<CPT><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, flow, out, B, C, H, W);
+    return check_launch("warp_fwd_kernel");
+}
+
+int pwc_warp_backward(const float* grad_out, const float* x, const float* flow, float* grad_x,
+                      float* grad_flow, int B, int C, int H, int W, cudaStream_t stream)
+{
+    if (!grad_out || !x || !flow) return fail("pwc_warp_backward: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("pwc_warp_backward: non-positive size");
+    if (!grad_x && !grad_flow) return 1;
+    if (grad_x &&
+        cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)B * C * H * W, stream) != cudaSuccess)
+        return fail("cudaMemsetAsync(grad_x): %s", cudaGetErrorString(cudaGetLastError()));
+    const size_t total = (size_t)B * H * W;
+    pwc::warp_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, grad_x, grad_flow, B, C, H, W);
+    return check_launch("warp_bwd_kernel");
+}
+
+int pwc_warpcorr_forward(const float* f1, const float* f2, const float* flow, float* out,
+                         float* warped_out, int B, int C, int H, int W, int pad_size,
+                         int kernel_size, int max_displacement, int stride1, int stride2, int act,
+                         float slope, cudaStream_t stream)
+{
+    if (!f1 || !f2 || !out) return fail("pwc_warpcorr_forward: null pointer");
+    pwc::CorrGeom g;
+    if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, stream);
+}
+
+long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_flow, int, int, int,
+                                          int, int)
+{
+    if (!has_flow) return 0;
+    // warped second operand + its gradient
+    return 2LL * (long long)sizeof(float) * B * C * H * W;
+}
+
+int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
+                          const float* flow, const float* out, float* grad_f1, float* grad_f2,
+                          float* grad_flow, void* workspace, long long workspace_bytes, int B,
+                          int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
+                          int stride1, int stride2, int act, float slope, cudaStream_t stream)
+{
+    if (!grad_out || !f1 || !f2 || !grad_f1 || !grad_f2) return fail("pwc_warpcorr_backward: null pointer");
+    if (act && !out) return fail("pwc_warpcorr_backward: act != 0 needs the forward output");
+    pwc::CorrGeom g;
+    if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    const float* gate = act ? out : nullptr;
+    if (!flow) return corr_backward_impl(grad_out, gate, f1, f2, grad_f1, grad_f2, g, slope, stream);
+    if (!grad_flow) return fail("pwc_warpcorr_backward: grad_flow is required when flow is given");
+    const long long need = pwc_warpcorr_backward_workspace(B, C, H, W, 1, pad_size, kernel_size,
+                                                           max_displacement, stride1, stride2);
+    if (!workspace || workspace_bytes < need)
+        return fail("pwc_warpcorr_backward: workspace of %lld bytes required, got %lld", need, workspace_bytes);
+    const size_t N = (size_t)B * C * H * W;
+    float* warped = static_cast<float*>(workspace);
+    float* gwarped = warped + N;
+    if (!pwc_warp_forward(f2, flow, warped, B, C, H, W, stream)) return 0;
+    if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream)) return 0;
+    return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
+}
+
+int Correlation_forward_cuda_kernel(float* output, int ob, int oc, int oh, int ow, int, int, int,
+                                    int, float* input1, int ic, int ih, int iw, int, int, int, int,
+                                    float* input2, int gc, int, int, int, int, float*, float*,
+                                    int pad_size, int kernel_size, int max_displacement,
+                                    int stride1, int stride2, int, cudaStream_t stream)
+{
+    if (!output || !input1 || !input2) return fail("Correlation_forward_cuda_kernel: null pointer");
+    if (gc != ic) return fail("input channel mismatch (%d vs %d)", ic, gc);
+    pwc::CorrGeom g;
+    if (!make_geom(g, ob, ic, ih, iw, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    if (oc != g.oc || oh != g.oh || ow != g.ow)
+        return fail("output is [%d,%d,%d,%d] but the parameters give [%d,%d,%d,%d]", ob, oc, oh, ow,
+                    ob, g.oc, g.oh, g.ow);
+    return forward_impl(input1, input2, nullptr, output, nullptr, g, 0, 0.0f, stream);
+}
+
+int Correlation_backward_cuda_kernel(float* gradOutput, int gob, int goc, int goh, int gow, int,
+                                     int, int, int, float* input1, int ic, int ih, int iw, int, int,
+                                     int, int, float* input2, int, int, int, int,
+                                     float* gradInput1, int, int, int, int, float* gradInput2,
+                                     int ggc, int, int, int, int, float*, float*, int pad_size,
+                                     int kernel_size, int max_displacement, int stride1,
+                                     int stride2, int, cudaStream_t stream)
+{
+    if (!gradOutput || !input1 || !input2 || !gradInput1 || !gradInput2)
+        return fail("Correlation_backward_cuda_kernel: null pointer");
+    if (ggc != ic) return fail("gradInput2 channel mismatch (%d vs %d)", ic, ggc);
+    pwc::CorrGeom g;
+    if (!make_geom(g, gob, ic, ih, iw, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    if (goc != g.oc || goh != g.oh || gow != g.ow)
+        return fail("gradOutput is [%d,%d,%d,%d] but the parameters give [%d,%d,%d,%d]", gob, goc,
+                    goh, gow, gob, g.oc, g.oh, g.ow);
+    return corr_backward_impl(gradOutput, nullptr, input1, input2, gradInput1, gradInput2, g, 0.0f, stream);
+}
+
+}  // extern "C"

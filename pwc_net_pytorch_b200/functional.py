@@ -1,0 +1,215 @@
+"""autograd Functions over the C ABI (PyTorch is plumbing here: device memory, streams, autograd).
+
+  CorrelationFunction      drop-in for correlation_package/functions/correlation.py:5-56
+  WarpFunction             WarpingLayer's arithmetic, modules.py:31-42 (+ its autograd)
+  WarpCorrelationFunction  model.py:80-84 fused: warp -> correlation -> optional leaky_relu_
+
+All tensors must be fp32 CUDA; inputs are made contiguous (the reference asserts contiguity for
+the inputs, functions/correlation.py:17-18, and silently assumes it for grad_output, :40-41).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check_inputs(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("pwc_net_pytorch_b200 ops are CUDA-only (sm_100a); there is no CPU path")
+        if t.dtype != torch.float32:
+            raise TypeError(f"expected float32, got {t.dtype} (the reference operator is fp32-only)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must be on the same device")
+    return dev
+
+
+def corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
+    """correlation_cuda.c:20-34."""
+    oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ok = _lib.load().pwc_corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1,
+                                           stride2, ctypes.byref(oc), ctypes.byref(oh),
+                                           ctypes.byref(ow))
+    _lib.check(ok, "pwc_corr_output_shape")
+    return oc.value, oh.value, ow.value
+
+
+def _dense_strides(t):
+    return [int(s) for s in t.stride()]
+
+
+class CorrelationFunction(Function):
+    """Same call signature and return convention as the reference Function; goes through the
+    legacy launcher symbols so the boundary exercised is exactly the reference's."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, pad_size=3, kernel_size=3, max_displacement=20, stride1=1,
+                stride2=2, corr_multiply=1):
+        dev = _check_inputs(input1, input2)
+        if input1.shape != input2.shape or input1.dim() != 4:
+            raise ValueError("input1/input2 must be 4-D tensors of identical shape")
+        input1 = input1.contiguous()
+        input2 = input2.contiguous()
+        ctx.save_for_backward(input1, input2)
+        ctx.params = (pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
+        B, C, H, W = input1.shape
+        oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+        output = torch.empty((B, oc, oh, ow), dtype=torch.float32, device=dev)
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            ok = L.Correlation_forward_cuda_kernel(
+                _ptr(output), B, oc, oh, ow, *_dense_strides(output),
+                _ptr(input1), C, H, W, *_dense_strides(input1),
+                _ptr(input2), C, *_dense_strides(input2),
+                None, None,
+                pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply, _stream())
+        _lib.check(ok, "Correlation_forward_cuda_kernel")
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input1, input2 = ctx.saved_tensors
+        pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply = ctx.params
+        grad_output = grad_output.contiguous()
+        _check_inputs(grad_output)
+        B, C, H, W = input1.shape
+        grad_input1 = torch.empty_like(input1)
+        grad_input2 = torch.empty_like(input2)
+        L = _lib.load()
+        with torch.cuda.device(input1.device):
+            ok = L.Correlation_backward_cuda_kernel(
+                _ptr(grad_output), *grad_output.shape, *_dense_strides(grad_output),
+                _ptr(input1), C, H, W, *_dense_strides(input1),
+                _ptr(input2), *_dense_strides(input2),
+                _ptr(grad_input1), *_dense_strides(grad_input1),
+                _ptr(grad_input2), C, *_dense_strides(grad_input2),
+                None, None,
+                pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply, _stream())
+        _lib.check(ok, "Correlation_backward_cuda_kernel")
+        return (grad_input1, grad_input2) + (None,) * 6
+
+
+class WarpFunction(Function):
+    @staticmethod
+    def forward(ctx, x, flow):
+        dev = _check_inputs(x, flow)
+        if x.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2 or \
+                flow.shape[0] != x.shape[0] or flow.shape[2:] != x.shape[2:]:
+            raise ValueError(f"x {tuple(x.shape)} / flow {tuple(flow.shape)}: expected [B,C,H,W] and [B,2,H,W]")
+        x = x.contiguous()
+        flow = flow.contiguous()
+        ctx.save_for_backward(x, flow)
+        out = torch.empty_like(x)
+        B, C, H, W = x.shape
+        with torch.cuda.device(dev):
+            ok = _lib.load().pwc_warp_forward(_ptr(x), _ptr(flow), _ptr(out), B, C, H, W, _stream())
+        _lib.check(ok, "pwc_warp_forward")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, flow = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        _check_inputs(grad_out)
+        B, C, H, W = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x.device):
+            ok = _lib.load().pwc_warp_backward(_ptr(grad_out), _ptr(x), _ptr(flow), _ptr(gx),
+                                               _ptr(gflow), B, C, H, W, _stream())
+        _lib.check(ok, "pwc_warp_backward")
+        return gx, gflow
+
+
+class WarpCorrelationFunction(Function):
+    """out = [leaky_relu]( Correlation(x1, warp(x2, flow)) ) in one launch; flow may be None."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, flow, pad_size, kernel_size, max_displacement, stride1, stride2,
+                act, slope, want_warped):
+        dev = _check_inputs(x1, x2, flow)
+        if x1.shape != x2.shape or x1.dim() != 4:
+            raise ValueError("x1/x2 must be 4-D tensors of identical shape")
+        B, C, H, W = x1.shape
+        if flow is not None and tuple(flow.shape) != (B, 2, H, W):
+            raise ValueError(f"flow must be [B,2,H,W] = {(B, 2, H, W)}, got {tuple(flow.shape)}")
+        x1 = x1.contiguous()
+        x2 = x2.contiguous()
+        flow = None if flow is None else flow.contiguous()
+        oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+        out = torch.empty((B, oc, oh, ow), dtype=torch.float32, device=dev)
+        warped = torch.empty_like(x2) if want_warped else None
+        with torch.cuda.device(dev):
+            ok = _lib.load().pwc_warpcorr_forward(
+                _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(warped), B, C, H, W,
+                pad_size, kernel_size, max_displacement, stride1, stride2,
+                int(bool(act)), float(slope), _stream())
+        _lib.check(ok, "pwc_warpcorr_forward")
+        ctx.params = (pad_size, kernel_size, max_displacement, stride1, stride2, bool(act), float(slope))
+        ctx.has_flow = flow is not None
+        if flow is None:
+            ctx.save_for_backward(x1, x2, out if act else None)
+        else:
+            ctx.save_for_backward(x1, x2, out if act else None, flow)
+        if want_warped:
+            ctx.mark_non_differentiable(warped)
+            return out, warped
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out, *unused):
+        pad_size, kernel_size, max_displacement, stride1, stride2, act, slope = ctx.params
+        if ctx.has_flow:
+            x1, x2, out, flow = ctx.saved_tensors
+        else:
+            x1, x2, out = ctx.saved_tensors
+            flow = None
+        grad_out = grad_out.contiguous()
+        _check_inputs(grad_out)
+        B, C, H, W = x1.shape
+        g1 = torch.empty_like(x1)
+        g2 = torch.empty_like(x2)
+        gflow = torch.empty_like(flow) if flow is not None else None
+        L = _lib.load()
+        ws_bytes = int(L.pwc_warpcorr_backward_workspace(B, C, H, W, int(flow is not None), pad_size,
+                                                         kernel_size, max_displacement, stride1, stride2))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x1.device) if ws_bytes else None
+        with torch.cuda.device(x1.device):
+            ok = L.pwc_warpcorr_backward(
+                _ptr(grad_out), _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(g1), _ptr(g2),
+                _ptr(gflow), _ptr(ws), ws_bytes, B, C, H, W,
+                pad_size, kernel_size, max_displacement, stride1, stride2,
+                int(act), float(slope), _stream())
+        _lib.check(ok, "pwc_warpcorr_backward")
+        return (g1, g2, gflow) + (None,) * 8
+
+
+def correlation(input1, input2, pad_size=3, kernel_size=3, max_displacement=20, stride1=1,
+                stride2=2, corr_multiply=1):
+    return CorrelationFunction.apply(input1, input2, pad_size, kernel_size, max_displacement,
+                                     stride1, stride2, corr_multiply)
+
+
+def warp(x, flow):
+    return WarpFunction.apply(x, flow)
+
+
+def warp_correlation(x1, x2, flow, pad_size=4, kernel_size=1, max_displacement=4, stride1=1,
+                     stride2=1, act=False, slope=0.01, return_warped=False):
+    return WarpCorrelationFunction.apply(x1, x2, flow, pad_size, kernel_size, max_displacement,
+                                         stride1, stride2, act, slope, return_warped)

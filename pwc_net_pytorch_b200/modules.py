@@ -1,0 +1,53 @@
+"""Host-side mirror of the hot-path modules of the reference's modules.py.
+
+  WarpingLayer(args).forward(x, flow)      modules.py:25-42 -- same constructor and call
+  FusedWarpCorrelation(...)(x1, x2, flow)  model.py:80-84 in one launch (new entry point)
+"""
+import torch.nn as nn
+
+from . import functional as PF
+
+
+class WarpingLayer(nn.Module):
+    """Backward warp of `x` by `flow` (pixel units of this level; channel 0 horizontal, channel 1
+    vertical): out[n,c,y,x] = bilinear_zero(x[n,c], x+u, y+v), i.e. modules.py:31-42 with
+    torch-0.4.0 grid_sample semantics.  `args` is kept for signature compatibility
+    (modules.py:27-29); only the tensors' own device is used -- no CPU grid is built or copied
+    per call (utils.py:3-7, modules.py:40)."""
+
+    def __init__(self, args=None):
+        super(WarpingLayer, self).__init__()
+        self.args = args
+
+    def forward(self, x, flow):
+        return PF.warp(x, flow)
+
+
+class FusedWarpCorrelation(nn.Module):
+    """corr = [leaky_relu_]( Correlation(x1, WarpingLayer(x2, flow)) ) without materialising the
+    warped features.  Defaults are the canonical PWC-Net cost volume (81 displacements, +-4 px);
+    `FusedWarpCorrelation.from_search_range(4)` gives the literal reference configuration
+    (model.py:24: pad 9, md 9, stride2 2 -> displacements {-8,-6,...,8})."""
+
+    def __init__(self, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1,
+                 corr_multiply=1, activation=False, negative_slope=0.01, return_warped=False):
+        super(FusedWarpCorrelation, self).__init__()
+        self.pad_size = pad_size
+        self.kernel_size = kernel_size
+        self.max_displacement = max_displacement
+        self.stride1 = stride1
+        self.stride2 = stride2
+        self.corr_multiply = corr_multiply
+        self.activation = activation
+        self.negative_slope = negative_slope
+        self.return_warped = return_warped
+
+    @classmethod
+    def from_search_range(cls, search_range, **kw):
+        return cls(pad_size=search_range * 2 + 1, kernel_size=1,
+                   max_displacement=search_range * 2 + 1, stride1=1, stride2=2, **kw)
+
+    def forward(self, x1, x2, flow=None):
+        return PF.warp_correlation(x1, x2, flow, self.pad_size, self.kernel_size,
+                                   self.max_displacement, self.stride1, self.stride2,
+                                   self.activation, self.negative_slope, self.return_warped)
