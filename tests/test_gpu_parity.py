@@ -1,0 +1,291 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes) behind the
+reference-shaped Python API, against the oracle on identical seeded inputs.
+
+Tolerance (north_star): per-level cost volumes and warped features within 1e-5 relative (fp32),
+judged in the max norm: ||new - ref||_inf <= 1e-5 * ||ref||_inf.
+Backward passes use fp32 atomics for the feature scatter, so their bound is the same relative
+tolerance rather than bit equality."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pwc_net_pytorch_b200 as pkg
+from pwc_net_pytorch_b200 import _lib
+from pwc_net_pytorch_b200 import functional as PF
+from oracle import c_oracle as co
+from oracle import ref_cuda
+from oracle import torch_ref as tr
+from util import CANON_CFG, GENERIC_CFGS, REF_CFG, make_inputs, max_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def to_dev(*arrs):
+    return [None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev()) for a in arrs]
+
+
+def test_extension_loaded_and_counts_launches():
+    L = _lib.load()
+    before = L.pwc_launch_count()
+    a, b, f = to_dev(*make_inputs(1, 4, 8, 8)[:3])
+    pkg.FusedWarpCorrelation()(a, b, f)
+    torch.cuda.synchronize()
+    assert L.pwc_launch_count() == before + 1      # one fused launch, nothing else
+    maps = open("/proc/self/maps").read()
+    assert "libpwc_b200.so" in maps
+
+
+# pyramid level shapes of a 384x448 pair (README.md:127-184) at small batch, plus ragged ones
+LEVEL_SHAPES = [(2, 192, 6, 7), (2, 196, 6, 7), (2, 128, 12, 14), (1, 96, 24, 28), (1, 64, 48, 56),
+                (1, 32, 96, 112), (1, 5, 9, 11), (1, 3, 33, 37), (3, 1, 8, 40), (1, 17, 2, 2)]
+
+
+@pytest.mark.parametrize("shape", LEVEL_SHAPES)
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_fused_forward_vs_oracle(shape, cfg):
+    B, C, H, W = shape
+    f1, f2, flow, _ = make_inputs(B, C, H, W, seed=B * 1000 + C + H)
+    ref, ref_w = co.warpcorr_forward(f1, f2, flow, *cfg, return_warped=True)
+    a, b, f = to_dev(f1, f2, flow)
+    m = pkg.FusedWarpCorrelation(*cfg, return_warped=True)
+    out, warped = m(a, b, f)
+    assert tuple(out.shape) == ref.shape
+    assert max_rel(out.cpu().numpy(), ref) < TOL
+    assert max_rel(warped.cpu().numpy(), ref_w) < TOL
+    # without the warped export the result is identical
+    out2 = pkg.FusedWarpCorrelation(*cfg)(a, b, f)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("kind", ["iid", "smooth", "integer", "zero"])
+@pytest.mark.parametrize("act", [False, True])
+def test_fused_forward_flow_kinds_and_activation(kind, act):
+    f1, f2, flow, _ = make_inputs(2, 32, 24, 28, seed=17, flow_sigma=3.0, flow_kind=kind)
+    for cfg in (REF_CFG, CANON_CFG):
+        ref = co.warpcorr_forward(f1, f2, flow, *cfg, act=act, slope=0.01)
+        out = pkg.FusedWarpCorrelation(*cfg, activation=act, negative_slope=0.01)(*to_dev(f1, f2, flow))
+        assert max_rel(out.cpu().numpy(), ref) < TOL
+        if kind == "zero":      # l == 0 of the pyramid loop (model.py:74-76): warp is the identity
+            plain = pkg.Correlation(*cfg)(*to_dev(f1, f2))
+            if act:
+                plain = torch.nn.functional.leaky_relu(plain, 0.01)
+            assert torch.equal(out, plain)
+
+
+@pytest.mark.parametrize("shape", LEVEL_SHAPES)
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_correlation_module_vs_oracle(shape, cfg):
+    B, C, H, W = shape
+    f1, f2, _, _ = make_inputs(B, C, H, W, seed=7)
+    ref = co.corr_forward(f1, f2, *cfg)
+    out = pkg.Correlation(*cfg, corr_multiply=1)(*to_dev(f1, f2))
+    assert max_rel(out.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("cfg", GENERIC_CFGS)
+def test_generic_parameters_vs_oracle(cfg):
+    f1, f2, flow, rng = make_inputs(2, 7, 13, 15, seed=23)
+    ref = co.corr_forward(f1, f2, *cfg)
+    a, b, f = to_dev(f1, f2, flow)
+    a.requires_grad_(); b.requires_grad_()
+    out = pkg.Correlation(*cfg)(a, b)
+    assert max_rel(out.detach().cpu().numpy(), ref) < TOL
+    reff = co.warpcorr_forward(f1, f2, flow, *cfg)
+    assert max_rel(pkg.FusedWarpCorrelation(*cfg)(a.detach(), b.detach(), f).cpu().numpy(), reff) < TOL
+    go = rng.standard_normal(ref.shape).astype(np.float32)
+    if cfg[3] == 1:
+        out.backward(to_dev(go)[0])
+        g1, g2 = co.corr_backward(go, f1, f2, *cfg)
+        assert max_rel(a.grad.cpu().numpy(), g1) < TOL
+        assert max_rel(b.grad.cpu().numpy(), g2) < TOL
+    else:
+        with pytest.raises(RuntimeError, match="stride1 == 1"):
+            out.backward(to_dev(go)[0])
+
+
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_forced_generic_equals_tiled(cfg):
+    f1, f2, flow, rng = make_inputs(2, 9, 17, 19, seed=29)
+    a, b, f = to_dev(f1, f2, flow)
+    L = _lib.load()
+    tiled = pkg.FusedWarpCorrelation(*cfg)(a, b, f)
+    prev = L.pwc_set_force_generic(1)
+    try:
+        generic = pkg.FusedWarpCorrelation(*cfg)(a, b, f)
+    finally:
+        L.pwc_set_force_generic(prev)
+    assert max_rel(tiled.cpu().numpy(), generic.cpu().numpy()) < 2e-6
+
+
+BWD_SHAPES = [(2, 192, 6, 7), (2, 196, 6, 7), (1, 96, 24, 28), (1, 32, 48, 56), (1, 5, 9, 11), (2, 3, 33, 37)]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_correlation_backward_vs_oracle(shape, cfg):
+    B, C, H, W = shape
+    f1, f2, _, rng = make_inputs(B, C, H, W, seed=31)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    g1, g2 = co.corr_backward(go, f1, f2, *cfg)
+    a, b, g = to_dev(f1, f2, go)
+    a.requires_grad_(); b.requires_grad_()
+    pkg.Correlation(*cfg)(a, b).backward(g)
+    assert max_rel(a.grad.cpu().numpy(), g1) < TOL
+    assert max_rel(b.grad.cpu().numpy(), g2) < TOL
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+@pytest.mark.parametrize("act", [False, True])
+def test_fused_backward_vs_oracle(shape, cfg, act):
+    B, C, H, W = shape
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=37, flow_sigma=2.0)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    fwd = co.warpcorr_forward(f1, f2, flow, *cfg, act=act, slope=0.01)
+    g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, fwd, *cfg, act=act, slope=0.01)
+    a, b, f, g = to_dev(f1, f2, flow, go)
+    for t in (a, b, f):
+        t.requires_grad_()
+    out = pkg.FusedWarpCorrelation(*cfg, activation=act, negative_slope=0.01)(a, b, f)
+    out.backward(g)
+    assert max_rel(a.grad.cpu().numpy(), g1) < TOL
+    assert max_rel(b.grad.cpu().numpy(), g2) < TOL
+    assert max_rel(f.grad.cpu().numpy(), gf) < TOL
+
+
+def test_warping_layer_vs_oracle_and_torch():
+    for shape in [(2, 192, 6, 7), (1, 32, 96, 112), (1, 3, 33, 37)]:
+        B, C, H, W = shape
+        _, f2, flow, rng = make_inputs(B, C, H, W, seed=41, flow_sigma=3.0)
+        x, f = to_dev(f2, flow)
+        x.requires_grad_(); f.requires_grad_()
+        y = pkg.WarpingLayer(None)(x, f)
+        assert max_rel(y.detach().cpu().numpy(), co.warp_forward(f2, flow, 0)) < TOL
+        # torch's own grid_sample with the 0.4.0 semantics, on the same device
+        assert max_rel(y.detach().cpu().numpy(), tr.warping_layer_port(x.detach(), f.detach()).cpu().numpy()) < 3e-5
+        go = rng.standard_normal(f2.shape).astype(np.float32)
+        y.backward(to_dev(go)[0])
+        gx, gf = co.warp_backward(go, f2, flow)
+        assert max_rel(x.grad.cpu().numpy(), gx) < TOL
+        assert max_rel(f.grad.cpu().numpy(), gf) < TOL
+
+
+def test_golden_reference_python_fixtures(golden):
+    """Reference-authored outputs (modules.WarpingLayer / CostVolumeLayer)."""
+    for name in ("tiny", "lvl6", "mid", "big_flow"):
+        f1, f2, flow = (golden[f"{name}/{k}"] for k in ("f1", "f2", "flow"))
+        C = f1.shape[1]
+        out, warped = pkg.FusedWarpCorrelation(*CANON_CFG, return_warped=True)(*to_dev(f1, f2, flow))
+        assert max_rel(warped.cpu().numpy(), golden[f"{name}/warp"]) < TOL
+        got = out.cpu().numpy()[:, tr.COSTVOLUME_PERM] * C
+        assert max_rel(got, golden[f"{name}/costvolume_of_warp"] * 81.0) < TOL
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref/libref_corr.so not built")
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG, (4, 3, 4, 1, 2), (4, 1, 4, 1, 2)])
+def test_against_reference_cuda_kernels_live(cfg):
+    """The reference's own kernels (compiled unchanged for sm_100a) on the same device."""
+    f1, f2, _, rng = make_inputs(2, 37, 12, 14, seed=43)
+    a, b = to_dev(f1, f2)
+    ref = ref_cuda.correlation_forward(a, b, *cfg)
+    a.requires_grad_(); b.requires_grad_()
+    out = pkg.Correlation(*cfg)(a, b)
+    assert max_rel(out.detach().cpu().numpy(), ref.cpu().numpy()) < TOL
+    go = torch.from_numpy(rng.standard_normal(tuple(ref.shape)).astype(np.float32)).to(dev())
+    r1, r2 = ref_cuda.correlation_backward(go, a.detach(), b.detach(), *cfg)
+    out.backward(go)
+    assert max_rel(a.grad.cpu().numpy(), r1.cpu().numpy()) < TOL
+    assert max_rel(b.grad.cpu().numpy(), r2.cpu().numpy()) < TOL
+
+
+def test_edge_cases():
+    f1, f2, flow, _ = make_inputs(1, 3, 6, 7)
+    a, b = to_dev(f1, f2)
+    far = torch.full((1, 2, 6, 7), 1000.0, device=dev())
+    assert not pkg.FusedWarpCorrelation()(a, b, far).any()
+    bad = torch.from_numpy(flow).to(dev())
+    bad[0, 0, 2, 3] = float("nan")
+    bad[0, 1, 1, 1] = float("inf")
+    w = pkg.WarpingLayer(None)(b, bad)
+    assert torch.isfinite(w).all() and not w[0, :, 2, 3].any() and not w[0, :, 1, 1].any()
+    out = pkg.FusedWarpCorrelation()(a, b, bad)
+    assert torch.isfinite(out).all()
+    # non-contiguous inputs are accepted (made dense), wrong dtypes / shapes are refused
+    nc = torch.randn(1, 6, 7, 3, device=dev()).permute(0, 3, 1, 2)
+    assert max_rel(pkg.Correlation(4, 1, 4, 1, 1)(nc, nc).cpu().numpy(),
+                   co.corr_forward(nc.cpu().numpy(), nc.cpu().numpy(), 4, 1, 4, 1, 1)) < TOL
+    with pytest.raises(TypeError):
+        pkg.Correlation(4, 1, 4, 1, 1)(a.double(), b.double())
+    with pytest.raises(ValueError):
+        pkg.FusedWarpCorrelation()(a, b, torch.zeros(1, 2, 5, 7, device=dev()))
+    with pytest.raises(RuntimeError, match="empty correlation output"):
+        pkg.Correlation(0, 1, 4, 1, 1)(a, b)
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 at full size (B=32, C=32, 96x112 and C=196, 6x7), through
+    size-independent properties instead of the (slow) CPU oracle:
+      * linearity in f1 and in f2;  * the centre channel with zero flow is mean_c f1*f2;
+      * zero flow == plain Correlation;  * <grad_out, J v> == <J^T grad_out, v> (adjointness);
+      * a spot check of 2 images against the oracle."""
+    torch.manual_seed(0)
+    for (B, C, H, W) in [(32, 32, 96, 112), (32, 196, 6, 7)]:
+        d = dev()
+        f1 = torch.randn(B, C, H, W, device=d)
+        f2 = torch.randn(B, C, H, W, device=d)
+        g2 = torch.randn(B, C, H, W, device=d)
+        flow = 2.0 * torch.randn(B, 2, H, W, device=d)
+        op = pkg.FusedWarpCorrelation(*CANON_CFG)
+        o1 = op(f1, f2, flow)
+        lin = op(f1, 2.0 * f2 + 0.5 * g2, flow)
+        assert max_rel((lin - 2.0 * o1 - 0.5 * op(f1, g2, flow)).cpu().numpy() + o1.cpu().numpy(), o1.cpu().numpy()) < 5e-6
+        z = torch.zeros_like(flow)
+        oz = op(f1, f2, z)
+        assert torch.equal(oz, pkg.Correlation(*CANON_CFG)(f1, f2))
+        assert max_rel(oz[:, 40].cpu().numpy(), (f1 * f2).mean(1).cpu().numpy()) < TOL
+        # adjointness of the backward kernels w.r.t. the forward (f1 and f2 directions)
+        a = f1.clone().requires_grad_(); b = f2.clone().requires_grad_()
+        go = torch.randn_like(o1)
+        op(a, b, flow).backward(go)
+        v1 = torch.randn_like(f1)
+        lhs = (go.double() * op(v1, f2, flow).double()).sum().item()
+        rhs = (a.grad.double() * v1.double()).sum().item()
+        assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0)
+        v2 = torch.randn_like(f2)
+        lhs = (go.double() * op(f1, v2, flow).double()).sum().item()
+        rhs = (b.grad.double() * v2.double()).sum().item()
+        assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0)
+        # oracle spot check on two images
+        sel = [0, B - 1]
+        ref = co.warpcorr_forward(f1[sel].cpu().numpy(), f2[sel].cpu().numpy(), flow[sel].cpu().numpy(), *CANON_CFG)
+        assert max_rel(o1[sel].cpu().numpy(), ref) < TOL
+
+
+def test_cuda_graph_capture_and_stream():
+    """The entry points enqueue on the caller's current stream and are graph-capturable
+    (no allocation, no sync inside the library)."""
+    f1, f2, flow, _ = make_inputs(2, 16, 24, 28, seed=47)
+    a, b, f = to_dev(f1, f2, flow)
+    op = pkg.FusedWarpCorrelation(*REF_CFG, activation=True)
+    eager = op(a, b, f)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            op(a, b, f)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        captured = op(a, b, f)
+    captured.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
