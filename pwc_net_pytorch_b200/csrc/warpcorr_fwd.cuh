@@ -140,17 +140,21 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                 const float4 w = sTapW[i];
                 const int2 o = sTapO[i];
                 float* dst = sW2 + hy * HP + hx;
+                // x2_warp export (model.py:107,113): interior pixels of the tile that are in the image
+                const int gy = y0t - R + hy, gx = x0t - R + hx;
+                const bool interior = warped_out != nullptr && hy >= R && hy < R + TH &&
+                                      hx >= R && hx < R + TW && gy < H && gx < W;
+                float* wo = interior ? warped_out + ((size_t)n * C + c0) * HW + (size_t)gy * W + gx
+                                     : nullptr;
                 if (o.x < 0) {
 #pragma unroll
-                    for (int c = 0; c < CK; ++c) dst[c * (HH * HP)] = 0.0f;
+                    for (int c = 0; c < CK; ++c) {
+                        dst[c * (HH * HP)] = 0.0f;
+                        if (wo && c0 + c < C) wo[(size_t)c * HW] = 0.0f;
+                    }
                 } else {
                     const int dx = o.y & 1, dyw = o.y >> 1;
                     const float* p00 = f2n + (size_t)c0 * HW + o.x;
-                    const bool interior = warped_out != nullptr && hy >= R && hy < R + TH &&
-                                          hx >= R && hx < R + TW;
-                    float* wo = interior ? warped_out + ((size_t)n * C + c0) * HW +
-                                           (size_t)(y0t - R + hy) * W + (x0t - R + hx)
-                                         : nullptr;
 #pragma unroll
                     for (int c = 0; c < CK; ++c) {
                         float v = 0.0f;
