@@ -119,6 +119,9 @@ long long pwc_launch_count(void);
 /* forces the generic (any kernel_size/stride) kernels even where a tiled fast path exists;
  * test hook, returns the previous value. */
 int pwc_set_force_generic(int on);
+/* disables the TMA-staged forward kernel (falls back to the plain tiled kernel); test hook,
+ * returns the previous value. */
+int pwc_set_disable_tma(int on);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,7 @@ EXPORTS = (
     "pwc_abi_version",
     "pwc_launch_count",
     "pwc_set_force_generic",
+    "pwc_set_disable_tma",
 )
 
 
@@ -68,6 +69,8 @@ def _declare(L):
     L.pwc_launch_count.restype = ctypes.c_longlong
     L.pwc_set_force_generic.argtypes = [_int]
     L.pwc_set_force_generic.restype = _int
+    L.pwc_set_disable_tma.argtypes = [_int]
+    L.pwc_set_disable_tma.restype = _int
 
 
 def load():

@@ -11,12 +11,14 @@
 #include "generic_kernels.cuh"
 #include "pwc_common.cuh"
 #include "warpcorr_fwd.cuh"
+#include "warpcorr_fwd_tma.cuh"
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_generic{0};
+std::atomic<int> g_disable_tma{0};
 
 int fail(const char* fmt, ...)
 {
@@ -84,6 +86,80 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
     return check_launch("warpcorr_fwd_kernel");
 }
 
+
+// ---- TMA path ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 4-D tensor map over a dense [B][C][H][W] fp32 tensor, box = (bw, bh, bc, 1); out-of-range box
+// elements (image border, channel tail) are filled with zeros by the TMA unit.
+bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int W, int bw, int bh, int bc)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool tma_eligible(const float* f1, const float* f2, const float* out, const pwc::CorrGeom& g)
+{
+    if (g_disable_tma.load()) return false;
+    if ((g.W & 3) != 0 || g.W < 16 || g.H < 8 || g.W >= 32760 || g.H >= 32760) return false;
+    if (((uintptr_t)f1 | (uintptr_t)f2 | (uintptr_t)out) & 15) return false;
+    return true;
+}
+
+// returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
+template <int S2, int CK, bool HAS_FLOW>
+int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+                   const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+{
+    using Cfg = pwc::TmaCfg<S2, CK>;
+    CUtensorMap m1, m2;
+    if (!make_nchw_map(&m1, f1, g.B, g.C, g.H, g.W, Cfg::F1W, Cfg::F1H, CK)) return -1;
+    if (!make_nchw_map(&m2, f2, g.B, g.C, g.H, g.W, HAS_FLOW ? Cfg::WW : Cfg::WP, HAS_FLOW ? Cfg::WH : Cfg::HH, CK))
+        return -1;
+    auto kern = pwc::warpcorr_fwd_tma_kernel<Cfg, HAS_FLOW>;
+    const size_t smem = Cfg::smem_bytes(HAS_FLOW);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured_dev = dev;
+    }
+    const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
+    const long long blocks = (long long)tiles_x * tiles_y * g.B;
+    if (blocks > 0x7fffffffLL) return fail("grid too large");
+    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(m1, m2, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y,
+                                                  act, slope);
+    return check_launch("warpcorr_fwd_tma_kernel");
+}
+
 template <int S2, bool HAS_FLOW>
 int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
                        float* warped, const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
@@ -97,6 +173,16 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
                  const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
 {
     if (fast_path(g)) {
+        if (tma_eligible(f1, f2, out, g)) {
+            int rc;
+            if (g.s2 == 1)
+                rc = flow ? launch_fwd_tma<1, 4, true>(f1, f2, flow, out, warped, g, act, slope, st)
+                          : launch_fwd_tma<1, 4, false>(f1, f2, flow, out, warped, g, act, slope, st);
+            else
+                rc = flow ? launch_fwd_tma<2, 2, true>(f1, f2, flow, out, warped, g, act, slope, st)
+                          : launch_fwd_tma<2, 2, false>(f1, f2, flow, out, warped, g, act, slope, st);
+            if (rc >= 0) return rc;
+        }
         if (g.s2 == 1)
             return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, out, warped, g, act, slope, st)
                         : dispatch_fwd_tiled<1, false>(f1, f2, flow, out, warped, g, act, slope, st);
@@ -164,6 +250,7 @@ const char* pwc_last_error(void) { return g_err; }
 int pwc_abi_version(void) { return PWC_B200_ABI_VERSION; }
 long long pwc_launch_count(void) { return g_launches.load(); }
 int pwc_set_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
+int pwc_set_disable_tma(int on) { return g_disable_tma.exchange(on ? 1 : 0); }
 
 int pwc_corr_output_shape(int H, int W, int pad_size, int kernel_size, int max_displacement,
                           int stride1, int stride2, int* out_channels, int* out_h, int* out_w)

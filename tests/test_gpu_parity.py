@@ -112,6 +112,48 @@ def test_generic_parameters_vs_oracle(cfg):
 
 
 @pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+@pytest.mark.parametrize("shape", [(2, 32, 48, 56), (1, 7, 16, 16), (1, 10, 24, 28), (2, 5, 9, 64), (1, 33, 40, 20)])
+def test_tma_kernel_equals_plain_tiled_kernel(cfg, shape):
+    """The TMA-staged warp-specialised kernel and the plain tiled kernel are two implementations
+    of the same arithmetic; W % 4 == 0 shapes take the TMA path by default."""
+    B, C, H, W = shape
+    f1, f2, flow, _ = make_inputs(B, C, H, W, seed=53)
+    a, b, f = to_dev(f1, f2, flow)
+    L = _lib.load()
+    outs = {}
+    for use_flow in (True, False):
+        tma = pkg.FusedWarpCorrelation(*cfg, return_warped=True)(a, b, f if use_flow else None)
+        prev = L.pwc_set_disable_tma(1)
+        try:
+            plain = pkg.FusedWarpCorrelation(*cfg, return_warped=True)(a, b, f if use_flow else None)
+        finally:
+            L.pwc_set_disable_tma(prev)
+        assert max_rel(tma[0].cpu().numpy(), plain[0].cpu().numpy()) < 2e-6
+        assert max_rel(tma[1].cpu().numpy(), plain[1].cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+@pytest.mark.parametrize("kind", ["large_smooth", "outliers", "huge_iid"])
+def test_tma_window_placement_and_global_fallback(cfg, kind):
+    """The f2 source window follows the flow's bounding box (large coherent motion), and samples
+    whose footprint leaves the window are gathered from global memory (outliers / huge spread)."""
+    B, C, H, W = 2, 12, 48, 64
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=59, flow_sigma=1.0, flow_kind="smooth")
+    if kind == "large_smooth":
+        flow = flow + np.array([17.3, -11.6], np.float32).reshape(1, 2, 1, 1)
+    elif kind == "outliers":
+        idx = rng.integers(0, H * W, size=40)
+        flat = flow.reshape(B, 2, -1)
+        flat[:, :, idx] += rng.choice([-30.0, 25.5, 40.25], size=(B, 2, 40)).astype(np.float32)
+    else:
+        flow = (12.0 * rng.standard_normal(flow.shape)).astype(np.float32)
+    ref, ref_w = co.warpcorr_forward(f1, f2, flow, *cfg, return_warped=True)
+    out, warped = pkg.FusedWarpCorrelation(*cfg, return_warped=True)(*to_dev(f1, f2, flow))
+    assert max_rel(warped.cpu().numpy(), ref_w) < TOL
+    assert max_rel(out.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
 def test_forced_generic_equals_tiled(cfg):
     f1, f2, flow, rng = make_inputs(2, 9, 17, 19, seed=29)
     a, b, f = to_dev(f1, f2, flow)
@@ -149,13 +191,16 @@ def test_fused_backward_vs_oracle(shape, cfg, act):
     B, C, H, W = shape
     f1, f2, flow, rng = make_inputs(B, C, H, W, seed=37, flow_sigma=2.0)
     go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
-    fwd = co.warpcorr_forward(f1, f2, flow, *cfg, act=act, slope=0.01)
-    g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, fwd, *cfg, act=act, slope=0.01)
     a, b, f, g = to_dev(f1, f2, flow, go)
     for t in (a, b, f):
         t.requires_grad_()
     out = pkg.FusedWarpCorrelation(*cfg, activation=act, negative_slope=0.01)(a, b, f)
     out.backward(g)
+    fwd = co.warpcorr_forward(f1, f2, flow, *cfg, act=act, slope=0.01)
+    assert max_rel(out.detach().cpu().numpy(), fwd) < TOL
+    # leaky_relu_'s backward is gated by the sign of the *stored* forward output; hand the oracle the
+    # same output so that elements within rounding of zero take the same branch on both sides
+    g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, out.detach().cpu().numpy(), *cfg, act=act, slope=0.01)
     assert max_rel(a.grad.cpu().numpy(), g1) < TOL
     assert max_rel(b.grad.cpu().numpy(), g2) < TOL
     assert max_rel(f.grad.cpu().numpy(), gf) < TOL
