@@ -15,7 +15,8 @@
 //     displacement row tj = wd - 4, lane (lr, ls) owns an 8-pixel strip and its 8x9 accumulators)
 //     correlate out of shared memory.  Producers and consumers meet only through mbarriers
 //     (full/empty per buffer); there is no __syncthreads in the channel loop.
-// Requires W % 4 == 0 and 16-byte aligned bases (TMA global strides are multiples of 16 bytes).
+// Requires W % 4 == 0 and 16-byte aligned bases (TMA global strides are multiples of 16 bytes);
+// every TMA start coordinate along x is kept a multiple of 4 pixels (see TmaCfg::WW).
 #pragma once
 #include <cuda.h>
 
@@ -88,7 +89,10 @@ struct TmaCfg {
     static constexpr int HH = TH + 2 * R, HWD = TW + 2 * R;   // warped tile + halo
     static constexpr int WP = HWD + 4;                     // pitch = 4 (mod 8): conflict-free 128-bit rows
     static constexpr int MARGIN = 8;                       // extra source pixels each side of the halo
-    static constexpr int WW = HWD + 2 * MARGIN, WH = HH + 2 * MARGIN;   // f2 source window (TMA box)
+    // f2 source window (TMA box).  +4 columns: the innermost TMA start coordinate must be a multiple
+    // of 16 bytes (measured on B200: a 4-D tiled fp32 load at x % 4 != 0 raises "illegal
+    // instruction"), so the window origin is rounded down to a multiple of 4 pixels.
+    static constexpr int WW = HWD + 2 * MARGIN + 4, WH = HH + 2 * MARGIN;
     static constexpr int F1W = TW + 4, F1H = TH;           // f1 box, pitch 20 = 4 (mod 8)
     static constexpr int NHALO = HH * HWD;
     static constexpr int WSPAN = PX + 2 * R;
@@ -239,7 +243,8 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
         {
             const int bx0 = bbox[0], by0 = bbox[1], bx1 = bbox[2], by1 = bbox[3];
             if (bx0 <= bx1) {
-                wx0 = (bx1 - bx0 + 1 <= WW) ? bx0 : (bx0 + bx1 + 1 - WW) / 2;
+                wx0 = bx0 & ~3;                                   // 16-byte aligned TMA start (also for x < 0)
+                if (bx1 - wx0 + 1 > WW) wx0 = ((bx0 + bx1 + 1 - WW) >> 1) & ~3;
                 wy0 = (by1 - by0 + 1 <= WH) ? by0 : (by0 + by1 + 1 - WH) / 2;
             }
         }
