@@ -173,6 +173,12 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
                  const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
 {
     if (fast_path(g)) {
+        if (warped && !flow) {   // no warp: x2_warp is x2 itself (model.py:80 with zero displacement)
+            if (cudaMemcpyAsync(warped, f2, sizeof(float) * (size_t)g.B * g.C * g.H * g.W,
+                                cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                return fail("cudaMemcpyAsync(warped_out): %s", cudaGetErrorString(cudaGetLastError()));
+            warped = nullptr;
+        }
         if (tma_eligible(f1, f2, out, g)) {
             int rc;
             if (g.s2 == 1)
