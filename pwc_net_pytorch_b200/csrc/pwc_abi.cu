@@ -141,6 +141,11 @@ int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* o
     if (!make_nchw_map(&m1, f1, g.B, g.C, g.H, g.W, Cfg::F1W, Cfg::F1H, CK)) return -1;
     if (!make_nchw_map(&m2, f2, g.B, g.C, g.H, g.W, HAS_FLOW ? Cfg::WW : Cfg::WP, HAS_FLOW ? Cfg::WH : Cfg::HH, CK))
         return -1;
+    CUtensorMap m3 = m2;   // unused without flow
+    if (HAS_FLOW) {
+        if (((uintptr_t)flow & 15) != 0) return -1;
+        if (!make_nchw_map(&m3, flow, g.B, 2, g.H, g.W, Cfg::HWD, Cfg::HH, 2)) return -1;
+    }
     auto kern = pwc::warpcorr_fwd_tma_kernel<Cfg, HAS_FLOW>;
     const size_t smem = Cfg::smem_bytes(HAS_FLOW);
     static thread_local int configured_dev = -1;
@@ -153,10 +158,15 @@ int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* o
         configured_dev = dev;
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
-    const long long blocks = (long long)tiles_x * tiles_y * g.B;
-    if (blocks > 0x7fffffffLL) return fail("grid too large");
-    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(m1, m2, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y,
-                                                  act, slope);
+    const long long ntiles = (long long)tiles_x * tiles_y * g.B;
+    if (ntiles > 0x3fffffffLL) return fail("grid too large");
+    static thread_local int sm_count = 0;
+    if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        sm_count = 148;
+    // persistent: one CTA per SM (148 on B200), each walks tiles blockIdx.x, blockIdx.x + grid, ...
+    const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
+    kern<<<grid, Cfg::NT, smem, st>>>(m1, m2, m3, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles,
+                                      act, slope);
     return check_launch("warpcorr_fwd_tma_kernel");
 }
 

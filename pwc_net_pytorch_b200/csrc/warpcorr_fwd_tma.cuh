@@ -10,11 +10,17 @@
 //   * the window is placed per CTA from the bounding box of the tile+halo sample positions
 //     (x+u, y+v), so large smooth flows cost nothing; a sample whose 2x2 footprint falls outside
 //     the window (rare outlier) is gathered from global memory instead;
-//   * the CTA is warp-specialised: 3 producer warps issue the TMA copies and evaluate the bilinear
-//     warp out of the window into a double-buffered warped tile; 9 consumer warps (warp wd owns
-//     displacement row tj = wd - 4, lane (lr, ls) owns an 8-pixel strip and its 8x9 accumulators)
-//     correlate out of shared memory.  Producers and consumers meet only through mbarriers
-//     (full/empty per buffer); there is no __syncthreads in the channel loop.
+//   * the CTA is persistent (one per SM, looping over 16x16 tiles) and warp-specialised into four
+//     roles that meet only through mbarriers (no __syncthreads after start-up):
+//       T  1 warp : issues every TMA request (flow tiles, f1 chunks, f2 windows), running ahead;
+//       P  1 warp : turns a flow tile into bilinear taps + the window origin (bbox by warp
+//                   shuffles), one tile ahead of the bilinear warps;
+//       B  5 warps: evaluate the bilinear warp out of the window into a ring of warped chunks
+//                   (taps live in registers for the whole tile, loads are batched for MLP);
+//       C  9 warps: warp wd owns displacement row tj = wd - 4, lane (lr, ls) owns an 8-pixel
+//                   strip and its 8x9 accumulators; correlate out of shared memory, then write
+//                   the cost volume.
+//     The stream of (tile, channel-chunk) work items is continuous across tiles.
 // Requires W % 4 == 0 and 16-byte aligned bases (TMA global strides are multiples of 16 bytes);
 // every TMA start coordinate along x is kept a multiple of 4 pixels (see TmaCfg::WW).
 #pragma once
@@ -83,9 +89,9 @@ struct TmaCfg {
     static constexpr int D = 9, S2 = S2_, CK = CK_, PX = 8;
     static constexpr int r = 4, R = r * S2;
     static constexpr int TW = 16, TH = 16;                 // output tile: 2 strips x 16 rows = 32 lanes
-    static constexpr int NCONS = 32 * D;                   // consumer threads: one warp per tj
-    static constexpr int NPROD = 96;                       // producer threads: TMA issue + bilinear warp
-    static constexpr int NT = NCONS + NPROD;               // 12 warps
+    static constexpr int NCONS = 32 * D;                   // C: one warp per tj
+    static constexpr int NBIL = 160;                       // B: bilinear warps
+    static constexpr int NT = NCONS + NBIL + 64;           // + P warp + T warp = 16 warps (regs are granted per 4 warps)
     static constexpr int HH = TH + 2 * R, HWD = TW + 2 * R;   // warped tile + halo
     static constexpr int WP = HWD + 4;                     // pitch = 4 (mod 8): conflict-free 128-bit rows
     static constexpr int MARGIN = 8;                       // extra source pixels each side of the halo
@@ -95,297 +101,413 @@ struct TmaCfg {
     static constexpr int WW = HWD + 2 * MARGIN + 4, WH = HH + 2 * MARGIN;
     static constexpr int F1W = TW + 4, F1H = TH;           // f1 box, pitch 20 = 4 (mod 8)
     static constexpr int NHALO = HH * HWD;
+    static constexpr int PXB = (NHALO + NBIL - 1) / NBIL;  // halo pixels per bilinear thread
+    static constexpr int PXP = (NHALO + 31) / 32;          // halo pixels per lane of the taps warp
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NWIN = 2, NF1 = 3, NW2F = 2, NW2P = 3;   // ring depths (flow / plain)
+    static constexpr int NS = 4;                           // warped-chunk ring (B -> C)
+    static constexpr int NF1 = 2 * NS;                     // f1 ring: requested NS work items ahead of use
+    static constexpr int NWIN = 3;                         // f2 window ring (T -> B)
     static constexpr int WIN_ELEMS = CK * WH * WW;
     static constexpr int F1_ELEMS = CK * F1H * F1W;
     static constexpr int W2_ELEMS = CK * HH * WP;
+    static constexpr int FLOW_ELEMS = 2 * HH * HWD;        // flow tile + halo (u and v), TMA box
     static constexpr uint32_t WIN_BYTES = WIN_ELEMS * 4, F1_BYTES = F1_ELEMS * 4, W2_BYTES = W2_ELEMS * 4;
+    static constexpr uint32_t FLOW_BYTES = FLOW_ELEMS * 4;
+    static constexpr int NBARS = 2 * NF1 + 2 * NS + 2 * NWIN + 8;
+    static constexpr int CTRL_BYTES = 512;                 // mbarriers + window origins
     static_assert(WP % 8 == 4 && F1W % 8 == 4, "pitches must be 4 mod 8 floats");
-    static_assert((WW * 4) % 16 == 0 && (F1W * 4) % 16 == 0 && (WP * 4) % 16 == 0, "TMA box rows are 16B multiples");
-    static_assert(WIN_BYTES % 128 == 0 && F1_BYTES % 128 == 0 && W2_BYTES % 128 == 0, "buffers stay 128B aligned");
+    static_assert((WW * 4) % 16 == 0 && (F1W * 4) % 16 == 0 && (WP * 4) % 16 == 0 && (HWD * 4) % 16 == 0,
+                  "TMA box rows are 16B multiples");
+    static_assert(WIN_BYTES % 128 == 0 && F1_BYTES % 128 == 0 && W2_BYTES % 128 == 0 && FLOW_BYTES % 128 == 0,
+                  "buffers stay 128B aligned");
+    static_assert(NBARS * 8 + 16 <= CTRL_BYTES, "control block too small");
 
     static constexpr size_t smem_bytes(bool has_flow)
     {
-        size_t b = 256;   // mbarriers + bbox scratch
-        b += (size_t)NF1 * F1_BYTES;
-        if (has_flow) {
-            b += (size_t)NWIN * WIN_BYTES + (size_t)NW2F * W2_BYTES;
-            b += (size_t)NHALO * (sizeof(float4) + sizeof(int));
-        } else {
-            b += (size_t)NW2P * W2_BYTES;
-        }
-        return b + 128;   // slack for the manual 128-byte alignment of the dynamic segment
+        size_t b = CTRL_BYTES + (size_t)NF1 * F1_BYTES + (size_t)NS * W2_BYTES;
+        if (has_flow)
+            b += (size_t)NWIN * WIN_BYTES + 2 * (size_t)FLOW_BYTES +
+                 2 * (size_t)NHALO * (sizeof(float4) + sizeof(int));
+        return b;
     }
 };
 
 constexpr int TAP_EMPTY = -1;      // every corner outside the image (or non-finite flow): value 0
 constexpr int TAP_GLOBAL = -2;     // footprint outside the staged window: gather from global memory
+constexpr int TAP_NONE = -3;       // padding entry of a thread's tap list (beyond NHALO)
+
+struct TileCoord { int n, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int tiles_y, int TH, int TW)
+{
+    TileCoord t;
+    const int tx = tile % tiles_x;
+    const int rest = tile / tiles_x;
+    t.x0 = tx * TW;
+    t.y0 = (rest % tiles_y) * TH;
+    t.n = rest / tiles_y;
+    return t;
+}
 
 template <class Cfg, bool HAS_FLOW>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2,
-                        const float* __restrict__ f2, const float* __restrict__ flow,
-                        float* __restrict__ out, float* __restrict__ warped_out,
-                        int C, int H, int W, int tiles_x, int tiles_y, int act, float slope)
+                        const __grid_constant__ CUtensorMap tmFlow, const float* __restrict__ f2,
+                        const float* __restrict__ flow, float* __restrict__ out, float* __restrict__ warped_out,
+                        int C, int H, int W, int tiles_x, int tiles_y, int ntiles, int act, float slope)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, HWD = Cfg::HWD;
     constexpr int WP = Cfg::WP, WW = Cfg::WW, WH = Cfg::WH, F1W = Cfg::F1W, F1H = Cfg::F1H;
-    constexpr int NHALO = Cfg::NHALO, WSPAN = Cfg::WSPAN, NCONS = Cfg::NCONS, NPROD = Cfg::NPROD;
-    constexpr int NWIN = Cfg::NWIN, NF1 = Cfg::NF1, NW2 = HAS_FLOW ? Cfg::NW2F : Cfg::NW2P;
+    constexpr int NHALO = Cfg::NHALO, WSPAN = Cfg::WSPAN, NCONS = Cfg::NCONS, NBIL = Cfg::NBIL;
+    constexpr int NS = Cfg::NS, NF1 = Cfg::NF1, NWIN = Cfg::NWIN, PXB = Cfg::PXB, PXP = Cfg::PXP;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* barF1 = reinterpret_cast<uint64_t*>(base);           // [NF1]  TMA f1 landed
-    uint64_t* barWin = barF1 + NF1;                                // [NWIN] TMA window landed
-    uint64_t* barW2Full = barWin + NWIN;                           // [3]    warped tile ready
-    uint64_t* barW2Empty = barW2Full + 3;                          // [3]    warped tile (and its f1) consumed
-    int* bbox = reinterpret_cast<int*>(base + 128);                // minx, miny, maxx, maxy
-    float* sF1 = reinterpret_cast<float*>(base + 256);
+    // No pointer<->integer round trips on this pointer: the compiler must keep the shared address space
+    // (otherwise every access below becomes a generic LD/ST instead of LDS/STS).
+    extern __shared__ __align__(1024) uint8_t base[];
+    uint64_t* barF1 = reinterpret_cast<uint64_t*>(base);   // [NF1]  TMA: f1 chunk landed           (T -> C)
+    uint64_t* barF1Free = barF1 + NF1;                     // [NF1]  f1 chunk consumed               (C -> T)
+    uint64_t* barFull = barF1Free + NF1;                   // [NS]   warped chunk ready              (B|TMA -> C)
+    uint64_t* barEmpty = barFull + NS;                     // [NS]   warped chunk consumed           (C -> B|T)
+    uint64_t* barWin = barEmpty + NS;                      // [NWIN] TMA: f2 window landed           (T -> B)
+    uint64_t* barWinFree = barWin + NWIN;                  // [NWIN] window read by every B thread   (B -> T)
+    uint64_t* barFlow = barWinFree + NWIN;                 // [2]    TMA: flow tile landed           (T -> P)
+    uint64_t* barFlowFree = barFlow + 2;                   // [2]    flow tile read                  (P -> T)
+    uint64_t* barTaps = barFlowFree + 2;                   // [2]    taps + window origin ready      (P -> B, T)
+    uint64_t* barTapsFree = barTaps + 2;                   // [2]    taps no longer needed           (B -> P)
+    int* worg = reinterpret_cast<int*>(base + Cfg::NBARS * 8);     // [2][2] window origin per tile parity
+    float* sF1 = reinterpret_cast<float*>(base + Cfg::CTRL_BYTES);
     float* sW2 = sF1 + NF1 * Cfg::F1_ELEMS;
-    float* sWin = sW2 + NW2 * Cfg::W2_ELEMS;                       // HAS_FLOW only
-    float4* sTapW = reinterpret_cast<float4*>(sWin + NWIN * Cfg::WIN_ELEMS);
-    int* sTapM = reinterpret_cast<int*>(sTapW + NHALO);
+    float* sWin = sW2 + NS * Cfg::W2_ELEMS;                        // HAS_FLOW only from here on
+    float* sFlow = sWin + NWIN * Cfg::WIN_ELEMS;                   // [2][2][HH][HWD]
+    float4* sTapW = reinterpret_cast<float4*>(sFlow + 2 * Cfg::FLOW_ELEMS);    // [2][NHALO]
+    int* sTapM = reinterpret_cast<int*>(sTapW + 2 * NHALO);                     // [2][NHALO]
 
     const int tid = threadIdx.x;
-    int t = blockIdx.x;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int n = t / tiles_y;
-    const int y0t = ty * TH, x0t = tx * TW;
     const size_t HW = (size_t)H * W;
     const int nchunks = (C + CK - 1) / CK;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; work items are (tile, chunk) pairs
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * nchunks;
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < NF1; ++i) mbar_init(&barF1[i], 1);
+        for (int i = 0; i < NF1; ++i) {
+            mbar_init(&barF1[i], 1);
+            mbar_init(&barF1Free[i], NCONS);
+        }
 #pragma unroll
-        for (int i = 0; i < NWIN; ++i) mbar_init(&barWin[i], 1);
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&barFull[i], HAS_FLOW ? NBIL : 1);
+            mbar_init(&barEmpty[i], NCONS);
+        }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(&barW2Full[i], HAS_FLOW ? NPROD : 1);
-            mbar_init(&barW2Empty[i], NCONS);
+        for (int i = 0; i < NWIN; ++i) {
+            mbar_init(&barWin[i], 1);
+            mbar_init(&barWinFree[i], NBIL);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&barFlow[i], 1);
+            mbar_init(&barFlowFree[i], 32);
+            mbar_init(&barTaps[i], 32);
+            mbar_init(&barTapsFree[i], NBIL);
         }
         fence_mbar_init();
-        bbox[0] = bbox[1] = 0x7fffffff;
-        bbox[2] = bbox[3] = -0x7fffffff;
     }
     __syncthreads();     // the only block-wide barrier; roles split below
 
-    if (tid >= NCONS) {
-        // =========================== producer warps ===========================
-        const int ptid = tid - NCONS;
-        if (ptid == 0) {
-            prefetch_tmap(&tmF1);
-            prefetch_tmap(&tmF2);
-            for (int k = 0; k < NF1 && k < nchunks; ++k) {
-                mbar_expect_tx(&barF1[k], Cfg::F1_BYTES);
-                tma_load_4d(sF1 + k * Cfg::F1_ELEMS, &tmF1, &barF1[k], x0t, y0t, k * CK, n);
-            }
-        }
+    if (tid >= NCONS + NBIL + 32) {
+        // ================================ T: TMA issue warp ================================
+        if (tid != NCONS + NBIL + 32) return;
+        prefetch_tmap(&tmF1);
+        prefetch_tmap(&tmF2);
+        auto request_f1 = [&](int j) {       // f1 chunk of work item j -> ring slot j % NF1
+            const TileCoord tj = tile_coord(blockIdx.x + (j / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
+            mbar_expect_tx(&barF1[j % NF1], Cfg::F1_BYTES);
+            tma_load_4d(sF1 + (j % NF1) * Cfg::F1_ELEMS, &tmF1, &barF1[j % NF1], tj.x0, tj.y0, (j % nchunks) * CK, tj.n);
+        };
         if (!HAS_FLOW) {
-            // plain correlation: the f2 tile + halo is the "warped" tile; TMA writes it directly
-            if (ptid == 0) {
-                for (int k = 0; k < nchunks; ++k) {
-                    const int b = k % NW2;
-                    if (k >= NW2) {
-                        mbar_wait(&barW2Empty[b], ((k / NW2) - 1) & 1);
-                        mbar_expect_tx(&barF1[k % NF1], Cfg::F1_BYTES);
-                        tma_load_4d(sF1 + (k % NF1) * Cfg::F1_ELEMS, &tmF1, &barF1[k % NF1], x0t, y0t, k * CK, n);
-                    }
-                    mbar_expect_tx(&barW2Full[b], Cfg::W2_BYTES);
-                    tma_load_4d(sW2 + b * Cfg::W2_ELEMS, &tmF2, &barW2Full[b], x0t - R, y0t - R, k * CK, n);
+            // plain correlation: the f2 tile + halo *is* the warped chunk; TMA writes it directly
+            for (int j = 0; j < NS && j < total; ++j) request_f1(j);
+            for (int g = 0; g < total; ++g) {
+                const int s = g % NS, jf = g + NS;
+                if (jf < total) {
+                    if (jf >= NF1) mbar_wait(&barF1Free[jf % NF1], ((jf / NF1) - 1) & 1);
+                    request_f1(jf);
                 }
+                const TileCoord tc = tile_coord(blockIdx.x + (g / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
+                if (g >= NS) mbar_wait(&barEmpty[s], ((g / NS) - 1) & 1);
+                mbar_expect_tx(&barFull[s], Cfg::W2_BYTES);
+                tma_load_4d(sW2 + s * Cfg::W2_ELEMS, &tmF2, &barFull[s], tc.x0 - R, tc.y0 - R, (g % nchunks) * CK, tc.n);
             }
             return;
         }
-
-        // ---- pass 1: sample positions of tile + halo, their bounding box ----
-        const float* un = flow + (size_t)n * 2 * HW;
-        int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -0x7fffffff, mxy = -0x7fffffff;
-        for (int i = ptid; i < NHALO; i += NPROD) {
-            const int hy = i / HWD, hx = i - hy * HWD;
-            const int y = y0t - R + hy, x = x0t - R + hx;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            int meta = TAP_EMPTY;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const float u = __ldg(un + (size_t)y * W + x);
-                const float v = __ldg(un + HW + (size_t)y * W + x);
-                const float sx = (float)x + u, sy = (float)y + v;
-                if (sx > -1.0f && sx < (float)W && sy > -1.0f && sy < (float)H) {
-                    const float fx = floorf(sx), fy = floorf(sy);
-                    const float ax = sx - fx, ay = sy - fy;
-                    const int x0 = (int)fx, y0 = (int)fy;
-                    w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
-                    meta = ((y0 + 1) << 16) | (x0 + 1);     // x0, y0 >= -1; H, W < 32760 checked on the host
-                    mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
-                    mny = min(mny, y0); mxy = max(mxy, y0 + 1);
-                }
-            }
-            sTapW[i] = w;
-            sTapM[i] = meta;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-        }
-        if ((ptid & 31) == 0) {
-            atomicMin(&bbox[0], mnx); atomicMin(&bbox[1], mny);
-            atomicMax(&bbox[2], mxx); atomicMax(&bbox[3], mxy);
-        }
-        producer_sync(NPROD);
-        // window origin: the bounding box if it fits, else centred on it (outliers go to global)
+        prefetch_tmap(&tmFlow);
+        auto request_flow = [&](int lt) {    // flow tile + halo of local tile lt -> sFlow[lt & 1]
+            const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+            mbar_expect_tx(&barFlow[lt & 1], Cfg::FLOW_BYTES);
+            tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 - R, tj.y0 - R, 0, tj.n);
+        };
+        if (my_tiles > 0) request_flow(0);
+        if (my_tiles > 1) request_flow(1);
+        for (int j = 0; j < NS && j < total; ++j) request_f1(j);
+        int win_tile = -1;      // last local tile whose window origin has been read
         int wx0 = 0, wy0 = 0;
-        {
-            const int bx0 = bbox[0], by0 = bbox[1], bx1 = bbox[2], by1 = bbox[3];
-            if (bx0 <= bx1) {
-                wx0 = bx0 & ~3;                                   // 16-byte aligned TMA start (also for x < 0)
-                if (bx1 - wx0 + 1 > WW) wx0 = ((bx0 + bx1 + 1 - WW) >> 1) & ~3;
-                wy0 = (by1 - by0 + 1 <= WH) ? by0 : (by0 + by1 + 1 - WH) / 2;
+        int jw = 0;             // next work item whose f2 window has not been requested
+        for (int g = 0; g < total; ++g) {
+            const int jf = g + NS;
+            if (jf < total) {
+                if (jf >= NF1) mbar_wait(&barF1Free[jf % NF1], ((jf / NF1) - 1) & 1);   // item jf - NF1 consumed
+                request_f1(jf);
             }
-        }
-        if (ptid == 0) {
-            for (int k = 0; k < NWIN && k < nchunks; ++k) {
-                mbar_expect_tx(&barWin[k], Cfg::WIN_BYTES);
-                tma_load_4d(sWin + k * Cfg::WIN_ELEMS, &tmF2, &barWin[k], wx0, wy0, k * CK, n);
-            }
-        }
-        // ---- pass 2: positions -> window-relative offsets (each thread owns the same taps in every pass) ----
-        for (int i = ptid; i < NHALO; i += NPROD) {
-            const int meta = sTapM[i];
-            if (meta >= 0) {
-                const int x0 = (meta & 0xffff) - 1, y0 = (meta >> 16) - 1;
-                const int rx = x0 - wx0, ry = y0 - wy0;
-                sTapM[i] = (rx >= 0 && rx + 1 < WW && ry >= 0 && ry + 1 < WH) ? ry * WW + rx : TAP_GLOBAL;
-            }
-        }
-
-        for (int k = 0; k < nchunks; ++k) {
-            const int c0 = k * CK, b = k % NW2;
-            if (k >= NW2) {
-                // consumers are done with chunk k - NW2: its warped tile and its f1 buffer are free
-                mbar_wait(&barW2Empty[b], ((k / NW2) - 1) & 1);
-                const int kf = k + 1;     // f1 chunks 0..NF1-1 were issued up front
-                if (ptid == 0 && kf >= NF1 && kf < nchunks) {
-                    mbar_expect_tx(&barF1[kf % NF1], Cfg::F1_BYTES);
-                    tma_load_4d(sF1 + (kf % NF1) * Cfg::F1_ELEMS, &tmF1, &barF1[kf % NF1], x0t, y0t, kf * CK, n);
-                }
-            }
-            const float* win = sWin + (k % NWIN) * Cfg::WIN_ELEMS;
-            float* w2buf = sW2 + b * Cfg::W2_ELEMS;
-            mbar_wait(&barWin[k % NWIN], (k / NWIN) & 1);
-            for (int i = ptid; i < NHALO; i += NPROD) {
-                const int hy = i / HWD, hx = i - hy * HWD;
-                const float4 w = sTapW[i];
-                const int meta = sTapM[i];
-                float v[CK];
-                if (meta >= 0) {
-                    const float* p = win + meta;
-#pragma unroll
-                    for (int c = 0; c < CK; ++c) {
-                        const float* q = p + c * (WH * WW);
-                        v[c] = fmaf(w.w, q[WW + 1], fmaf(w.z, q[WW], fmaf(w.y, q[1], w.x * q[0])));
+            for (; jw < total && jw < g + NWIN; ++jw) {
+                const int lt = jw / nchunks;
+                if (lt > win_tile) {
+                    if (lt + 1 < my_tiles && lt + 1 >= 2) {
+                        mbar_wait(&barFlowFree[(lt + 1) & 1], ((lt - 1) >> 1) & 1);   // P is done with tile lt - 1's flow
+                        request_flow(lt + 1);
                     }
-                } else if (meta == TAP_EMPTY) {
-#pragma unroll
-                    for (int c = 0; c < CK; ++c) v[c] = 0.0f;
-                } else {
-                    // outlier: recompute the tap from the flow and gather from global memory
-                    const int y = y0t - R + hy, x = x0t - R + hx;
-                    const Tap tp = make_tap((float)x + __ldg(un + (size_t)y * W + x),
-                                            (float)y + __ldg(un + HW + (size_t)y * W + x), H, W);
-#pragma unroll
-                    for (int c = 0; c < CK; ++c)
-                        v[c] = (c0 + c < C && tp.off >= 0)
-                                   ? tap_sample(tp, f2 + ((size_t)n * C + c0 + c) * HW) : 0.0f;
+                    mbar_wait(&barTaps[lt & 1], (lt >> 1) & 1);
+                    wx0 = worg[2 * (lt & 1)]; wy0 = worg[2 * (lt & 1) + 1];
+                    win_tile = lt;
                 }
-                float* dst = w2buf + hy * WP + hx;
-#pragma unroll
-                for (int c = 0; c < CK; ++c) dst[c * (HH * WP)] = v[c];
-                if (warped_out != nullptr) {     // x2_warp export (model.py:107,113)
-                    const int gy = y0t - R + hy, gx = x0t - R + hx;
-                    if (hy >= R && hy < R + TH && hx >= R && hx < R + TW && gy < H && gx < W) {
-                        float* wo = warped_out + ((size_t)n * C + c0) * HW + (size_t)gy * W + gx;
-#pragma unroll
-                        for (int c = 0; c < CK; ++c)
-                            if (c0 + c < C) wo[(size_t)c * HW] = v[c];
-                    }
-                }
-            }
-            mbar_arrive(&barW2Full[b]);          // release: this thread's part of warped tile k is written
-            if (k + NWIN < nchunks) {
-                producer_sync(NPROD);            // every producer has finished reading window k
-                if (ptid == 0) {
-                    const int kk = k + NWIN;
-                    mbar_expect_tx(&barWin[kk % NWIN], Cfg::WIN_BYTES);
-                    tma_load_4d(sWin + (kk % NWIN) * Cfg::WIN_ELEMS, &tmF2, &barWin[kk % NWIN], wx0, wy0, kk * CK, n);
-                }
+                if (jw >= NWIN) mbar_wait(&barWinFree[jw % NWIN], ((jw / NWIN) - 1) & 1);   // B is done with item jw - NWIN
+                const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+                mbar_expect_tx(&barWin[jw % NWIN], Cfg::WIN_BYTES);
+                tma_load_4d(sWin + (jw % NWIN) * Cfg::WIN_ELEMS, &tmF2, &barWin[jw % NWIN], wx0, wy0,
+                            (jw % nchunks) * CK, tj.n);
             }
         }
         return;
     }
 
-    // =========================== consumer warps ===========================
-    const int lane = tid & 31, wd = tid >> 5;     // wd: displacement row, tj = wd - r
-    const int lr = lane & 15, ls = lane >> 4;     // rows fastest: a quarter warp spans 8 rows of one strip
-    float acc[PX][D];
-#pragma unroll
-    for (int p = 0; p < PX; ++p)
-#pragma unroll
-        for (int d = 0; d < D; ++d) acc[p][d] = 0.0f;
-
-    for (int k = 0; k < nchunks; ++k) {
-        const int b = k % NW2;
-        mbar_wait(&barF1[k % NF1], (k / NF1) & 1);
-        mbar_wait(&barW2Full[b], (k / NW2) & 1);
-        const float* pf = sF1 + (k % NF1) * Cfg::F1_ELEMS + lr * F1W + ls * PX;
-        const float* pw = sW2 + b * Cfg::W2_ELEMS + (lr + wd * S2) * WP + ls * PX;
-#pragma unroll
-        for (int c = 0; c < CK; ++c) {
-            float f[PX];
-#pragma unroll
-            for (int q = 0; q < PX / 4; ++q) {
-                const float4 v4 = *reinterpret_cast<const float4*>(pf + c * (F1H * F1W) + 4 * q);
-                f[4 * q] = v4.x; f[4 * q + 1] = v4.y; f[4 * q + 2] = v4.z; f[4 * q + 3] = v4.w;
+    if (tid >= NCONS + NBIL) {
+        // ================================ P: taps warp ================================
+        if (!HAS_FLOW) return;
+        const int lane = tid & 31;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int par = lt & 1;
+            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+            mbar_wait(&barFlow[par], (lt >> 1) & 1);
+            if (lt >= 2) mbar_wait(&barTapsFree[par], ((lt >> 1) - 1) & 1);   // B finished tile lt - 2
+            const float* sfl = sFlow + par * Cfg::FLOW_ELEMS;
+            float4* tapW = sTapW + par * NHALO;
+            int* tapM = sTapM + par * NHALO;
+            // pass 1: sample positions of tile + halo and their bounding box (pixels outside the image are
+            // skipped by coordinate; the TMA zero fill of the flow tile is never interpreted)
+            int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -0x7fffffff, mxy = -0x7fffffff;
+#pragma unroll 4
+            for (int j = 0; j < PXP; ++j) {
+                const int i = lane + 32 * j;
+                if (i < NHALO) {
+                    const int hy = i / HWD, hx = i - hy * HWD;
+                    const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int meta = TAP_EMPTY;
+                    if (y >= 0 && y < H && x >= 0 && x < W) {
+                        const float sx = (float)x + sfl[i], sy = (float)y + sfl[NHALO + i];
+                        if (sx > -1.0f && sx < (float)W && sy > -1.0f && sy < (float)H) {
+                            const float fx = floorf(sx), fy = floorf(sy);
+                            const float ax = sx - fx, ay = sy - fy;
+                            const int x0 = (int)fx, y0 = (int)fy;
+                            w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
+                            meta = ((y0 + 1) << 16) | (x0 + 1);   // x0, y0 >= -1; H, W < 32760 (host check)
+                            mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
+                            mny = min(mny, y0); mxy = max(mxy, y0 + 1);
+                        }
+                    }
+                    tapW[i] = w;
+                    tapM[i] = meta;
+                }
             }
+            mbar_arrive(&barFlowFree[par]);      // this lane no longer reads sFlow[par]
 #pragma unroll
-            for (int q = 0; q < WSPAN / 4; ++q) {
-                const float4 v4 = *reinterpret_cast<const float4*>(pw + c * (HH * WP) + 4 * q);
-                const float wq[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = 4 * q + e;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const int p = j - d * S2;
-                        if (p >= 0 && p < PX) acc[p][d] = fmaf(f[p], wq[e], acc[p][d]);
+            for (int o = 16; o > 0; o >>= 1) {
+                mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+                mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+                mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+                mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            }
+            // window origin: the bounding box if it fits, else centred on it (outliers -> global gather)
+            int wx0 = 0, wy0 = 0;
+            if (mnx <= mxx) {
+                wx0 = mnx & ~3;                                   // 16-byte aligned TMA start (also for x < 0)
+                if (mxx - wx0 + 1 > WW) wx0 = ((mnx + mxx + 1 - WW) >> 1) & ~3;
+                wy0 = (mxy - mny + 1 <= WH) ? mny : (mny + mxy + 1 - WH) / 2;
+            }
+            // pass 2: positions -> window-relative offsets (each lane revisits exactly the taps it wrote)
+#pragma unroll 4
+            for (int j = 0; j < PXP; ++j) {
+                const int i = lane + 32 * j;
+                if (i < NHALO) {
+                    const int meta = tapM[i];
+                    if (meta >= 0) {
+                        const int x0 = (meta & 0xffff) - 1, y0 = (meta >> 16) - 1;
+                        const int rx = x0 - wx0, ry = y0 - wy0;
+                        tapM[i] = (rx >= 0 && rx + 1 < WW && ry >= 0 && ry + 1 < WH) ? ry * WW + rx : TAP_GLOBAL;
                     }
                 }
             }
+            if (lane == 0) { worg[2 * par] = wx0; worg[2 * par + 1] = wy0; }
+            mbar_arrive(&barTaps[par]);          // release: taps[par] and worg[par] are complete
         }
-        mbar_arrive(&barW2Empty[b]);     // chunk k (warped tile b and f1 buffer k % NF1) consumed
+        return;
     }
 
-    // ---- epilogue: 1/C (correlation_cuda_kernel.cu:65,100), optional LeakyReLU (model.py:84) ----
-    const int y = y0t + lr;
-    const int xs = x0t + ls * PX;
-    if (y < H && xs < W) {     // W % 4 == 0 and xs % 8 == 0: a strip is fully inside or ends on a multiple of 4
-        const float nelems = (float)C;
+    if (tid >= NCONS) {
+        // ================================ B: bilinear warps ================================
+        if (!HAS_FLOW) return;
+        const int btid = tid - NCONS;
+        float4 tw[PXB];          // this thread's taps for the current tile (registers for all its chunks)
+        int toff[PXB];           // window offset (0 for empty taps: weights are 0), or TAP_NONE / TAP_GLOBAL
+        int tdst[PXB];           // destination offset in the warped chunk
+        bool any_global = false;
+        for (int g = 0; g < total; ++g) {
+            const int lt = g / nchunks, k = g - lt * nchunks, par = lt & 1, s = g % NS;
+            const int c0 = k * CK;
+            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+            if (k == 0) {
+                mbar_wait(&barTaps[par], (lt >> 1) & 1);
+                any_global = false;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            float* o = out + (((size_t)n * (D * D) + (wd * D + d)) * H + y) * W + xs;
-            float v[PX];
-#pragma unroll
-            for (int p = 0; p < PX; ++p) {
-                v[p] = acc[p][d] / nelems;
-                if (act) v[p] = leaky(v[p], slope);
+                for (int j = 0; j < PXB; ++j) {
+                    const int i = btid + j * NBIL;
+                    const bool valid = i < NHALO;
+                    const int ii = valid ? i : 0;
+                    const int hy = ii / HWD, hx = ii - hy * HWD;
+                    tw[j] = sTapW[par * NHALO + ii];
+                    const int meta = sTapM[par * NHALO + ii];
+                    tdst[j] = hy * WP + hx;
+                    toff[j] = !valid ? TAP_NONE : (meta == TAP_EMPTY ? 0 : meta);
+                    any_global |= valid && meta == TAP_GLOBAL;
+                }
             }
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            if (xs + 4 < W) *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            if (g >= NS) mbar_wait(&barEmpty[s], ((g / NS) - 1) & 1);    // consumers released warped slot s
+            mbar_wait(&barWin[g % NWIN], (g / NWIN) & 1);
+            const float* win = sWin + (g % NWIN) * Cfg::WIN_ELEMS;
+            float* w2buf = sW2 + s * Cfg::W2_ELEMS;
+            float v[PXB][CK];
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                const float* p = win + (toff[j] >= 0 ? toff[j] : 0);     // empty / none / global: a safe address
+#pragma unroll
+                for (int c = 0; c < CK; ++c) {
+                    const float* q = p + c * (WH * WW);
+                    v[j][c] = fmaf(tw[j].w, q[WW + 1], fmaf(tw[j].z, q[WW], fmaf(tw[j].y, q[1], tw[j].x * q[0])));
+                }
+            }
+            if (any_global) {
+                // outliers: recompute the tap from the flow and gather from global memory
+                const float* un = flow + (size_t)tc.n * 2 * HW;
+#pragma unroll
+                for (int j = 0; j < PXB; ++j) {
+                    if (toff[j] == TAP_GLOBAL) {
+                        const int i = btid + j * NBIL;
+                        const int hy = i / HWD, hx = i - hy * HWD;
+                        const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
+                        const Tap tp = make_tap((float)x + __ldg(un + (size_t)y * W + x),
+                                                (float)y + __ldg(un + HW + (size_t)y * W + x), H, W);
+#pragma unroll
+                        for (int c = 0; c < CK; ++c)
+                            v[j][c] = (c0 + c < C && tp.off >= 0)
+                                          ? tap_sample(tp, f2 + ((size_t)tc.n * C + c0 + c) * HW) : 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                if (toff[j] != TAP_NONE) {
+                    float* dst = w2buf + tdst[j];
+#pragma unroll
+                    for (int c = 0; c < CK; ++c) dst[c * (HH * WP)] = v[j][c];
+                }
+            }
+            if (warped_out != nullptr) {     // x2_warp export (model.py:107,113)
+#pragma unroll
+                for (int j = 0; j < PXB; ++j) {
+                    const int i = btid + j * NBIL;
+                    const int hy = i / HWD, hx = i - hy * HWD;
+                    const int gy = tc.y0 - R + hy, gx = tc.x0 - R + hx;
+                    if (toff[j] != TAP_NONE && hy >= R && hy < R + TH && hx >= R && hx < R + TW && gy < H && gx < W) {
+                        float* wo = warped_out + ((size_t)tc.n * C + c0) * HW + (size_t)gy * W + gx;
+#pragma unroll
+                        for (int c = 0; c < CK; ++c)
+                            if (c0 + c < C) wo[(size_t)c * HW] = v[j][c];
+                    }
+                }
+            }
+            mbar_arrive(&barFull[s]);                 // release: this thread's part of warped chunk g is written
+            mbar_arrive(&barWinFree[g % NWIN]);       // and it no longer reads window g % NWIN
+            if (k == nchunks - 1) mbar_arrive(&barTapsFree[par]);
+        }
+        return;
+    }
+
+    // ================================ C: correlation warps ================================
+    const int lane = tid & 31, wd = tid >> 5;     // wd: displacement row, tj = wd - r
+    const int lr = lane & 15, ls = lane >> 4;     // rows fastest: a quarter warp spans 8 rows of one strip
+    // 1/C (correlation_cuda_kernel.cu:65,100 divide by nelems; a correctly rounded reciprocal and one
+    // multiply differ from the division by at most 1 ulp, far inside the 1e-5 tolerance)
+    const float inv_nelems = __frcp_rn((float)C);
+    int g = 0;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+        const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+        float acc[PX][D];
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc[p][d] = 0.0f;
+
+        for (int k = 0; k < nchunks; ++k, ++g) {
+            const int s = g % NS, sf = g % NF1;
+            mbar_wait(&barF1[sf], (g / NF1) & 1);
+            mbar_wait(&barFull[s], (g / NS) & 1);
+            const float* pf = sF1 + sf * Cfg::F1_ELEMS + lr * F1W + ls * PX;
+            const float* pw = sW2 + s * Cfg::W2_ELEMS + (lr + wd * S2) * WP + ls * PX;
+#pragma unroll
+            for (int c = 0; c < CK; ++c) {
+                float f[PX];
+#pragma unroll
+                for (int q = 0; q < PX / 4; ++q) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(pf + c * (F1H * F1W) + 4 * q);
+                    f[4 * q] = v4.x; f[4 * q + 1] = v4.y; f[4 * q + 2] = v4.z; f[4 * q + 3] = v4.w;
+                }
+                // walk the warped row one 128-bit quad at a time: only 4 of its values are live at once
+#pragma unroll
+                for (int q = 0; q < WSPAN / 4; ++q) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(pw + c * (HH * WP) + 4 * q);
+                    const float wq[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * q + e;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const int p = j - d * S2;
+                            if (p >= 0 && p < PX) acc[p][d] = fmaf(f[p], wq[e], acc[p][d]);
+                        }
+                    }
+                }
+            }
+            mbar_arrive(&barEmpty[s]);       // warped chunk slot s consumed
+            mbar_arrive(&barF1Free[sf]);     // f1 chunk slot sf consumed
+        }
+
+        // ---- epilogue: 1/C, optional LeakyReLU (model.py:84) ----
+        const int y = tc.y0 + lr;
+        const int xs = tc.x0 + ls * PX;
+        if (y < H && xs < W) {   // W % 4 == 0 and xs % 8 == 0: a strip is fully inside or ends on a multiple of 4
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float* o = out + (((size_t)tc.n * (D * D) + (wd * D + d)) * H + y) * W + xs;
+                float v[PX];
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    v[p] = acc[p][d] * inv_nelems;
+                    if (act) v[p] = leaky(v[p], slope);
+                }
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                if (xs + 4 < W) *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
         }
     }
 }
