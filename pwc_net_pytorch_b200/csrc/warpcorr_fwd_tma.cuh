@@ -75,6 +75,13 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map)
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane and instruction.
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -449,6 +456,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     // 1/C (correlation_cuda_kernel.cu:65,100 divide by nelems; a correctly rounded reciprocal and one
     // multiply differ from the division by at most 1 ulp, far inside the 1e-5 tolerance)
     const float inv_nelems = __frcp_rn((float)C);
+    const bool out_32B_aligned = ((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
         const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
@@ -464,28 +472,48 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
             mbar_wait(&barFull[s], (g / NS) & 1);
             const float* pf = sF1 + sf * Cfg::F1_ELEMS + lr * F1W + ls * PX;
             const float* pw = sW2 + s * Cfg::W2_ELEMS + (lr + wd * S2) * WP + ls * PX;
+            // Software-pipelined at 128-bit granularity: a warped-row quad is reloaded for the next
+            // channel right after its last use, so every LDS has a whole channel of FFMAs to land.
+            float f[PX], w[WSPAN];
+#pragma unroll
+            for (int q = 0; q < PX / 4; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(pf + 4 * q);
+                f[4 * q] = v4.x; f[4 * q + 1] = v4.y; f[4 * q + 2] = v4.z; f[4 * q + 3] = v4.w;
+            }
+#pragma unroll
+            for (int q = 0; q < WSPAN / 4; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(pw + 4 * q);
+                w[4 * q] = v4.x; w[4 * q + 1] = v4.y; w[4 * q + 2] = v4.z; w[4 * q + 3] = v4.w;
+            }
 #pragma unroll
             for (int c = 0; c < CK; ++c) {
-                float f[PX];
+                float fn[PX];
+                if (c + 1 < CK) {
 #pragma unroll
-                for (int q = 0; q < PX / 4; ++q) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(pf + c * (F1H * F1W) + 4 * q);
-                    f[4 * q] = v4.x; f[4 * q + 1] = v4.y; f[4 * q + 2] = v4.z; f[4 * q + 3] = v4.w;
+                    for (int q = 0; q < PX / 4; ++q) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(pf + (c + 1) * (F1H * F1W) + 4 * q);
+                        fn[4 * q] = v4.x; fn[4 * q + 1] = v4.y; fn[4 * q + 2] = v4.z; fn[4 * q + 3] = v4.w;
+                    }
                 }
-                // walk the warped row one 128-bit quad at a time: only 4 of its values are live at once
 #pragma unroll
                 for (int q = 0; q < WSPAN / 4; ++q) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(pw + c * (HH * WP) + 4 * q);
-                    const float wq[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int j = 4 * q + e;
+                        const int jj = 4 * q + e;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
-                            const int p = j - d * S2;
-                            if (p >= 0 && p < PX) acc[p][d] = fmaf(f[p], wq[e], acc[p][d]);
+                            const int p = jj - d * S2;
+                            if (p >= 0 && p < PX) acc[p][d] = fmaf(f[p], w[jj], acc[p][d]);
                         }
                     }
+                    if (c + 1 < CK) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(pw + (c + 1) * (HH * WP) + 4 * q);
+                        w[4 * q] = v4.x; w[4 * q + 1] = v4.y; w[4 * q + 2] = v4.z; w[4 * q + 3] = v4.w;
+                    }
+                }
+                if (c + 1 < CK) {
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) f[p] = fn[p];
                 }
             }
             mbar_arrive(&barEmpty[s]);       // warped chunk slot s consumed
@@ -496,6 +524,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
         const int y = tc.y0 + lr;
         const int xs = tc.x0 + ls * PX;
         if (y < H && xs < W) {   // W % 4 == 0 and xs % 8 == 0: a strip is fully inside or ends on a multiple of 4
+            const bool wide = out_32B_aligned && xs + PX <= W;     // the strip is one aligned 32-byte sector
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 float* o = out + (((size_t)tc.n * (D * D) + (wd * D + d)) * H + y) * W + xs;
@@ -505,8 +534,12 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                     v[p] = acc[p][d] * inv_nelems;
                     if (act) v[p] = leaky(v[p], slope);
                 }
-                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                if (xs + 4 < W) *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (wide) {
+                    st_global_v8(o, v);
+                } else {
+                    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (xs + 4 < W) *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
             }
         }
     }
