@@ -253,6 +253,7 @@ def run_native(args):
 
     import pwc_net_pytorch_b200 as pkg
     from pwc_net_pytorch_b200 import _lib
+    from pwc_net_pytorch_b200 import parallel
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback exists)")
@@ -335,11 +336,8 @@ def run_native(args):
     fwd_ms = [a.elapsed_time(b) for a, b in ev_pairs]
     fwd_l2_ms = sum(fwd_ms) / len(fwd_ms)
 
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-    value = world * PAIRS_PER_GPU * args.steps / (ms_total_max * 1e-3)
+    # whole-job pairs/s = pairs of all ranks / slowest rank's device time (no data-path collective)
+    value, ms_total_max = parallel.job_throughput(PAIRS_PER_GPU * args.steps, ms_total, dev)
 
     # ---- e2e: same step, every input from pinned host memory, every result back to the host ----
     host = {}
@@ -375,10 +373,7 @@ def run_native(args):
         e2e_step()
     e_end.record()
     barrier()
-    te = torch.tensor([e_start.elapsed_time(e_end)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * PAIRS_PER_GPU * e2e_steps / (float(te.item()) * 1e-3)
+    e2e_value, _ = parallel.job_throughput(PAIRS_PER_GPU * e2e_steps, e_start.elapsed_time(e_end), dev)
 
     # ---- per-kernel breakdown + extras (rank 0, outside the timed region) ----
     extras = {}
@@ -413,7 +408,7 @@ def run_native(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {
-                "kernel": "warpcorr_fwd_kernel (fused warp+corr forward, level-2 shape B=32 C=32 96x112)",
+                "kernel": "warpcorr_fwd_tma_kernel (fused warp+corr forward, level-2 shape B=32 C=32 96x112)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fwd_bytes(B, C, H, W), "avg_launch_ms": fwd_l2_ms,
