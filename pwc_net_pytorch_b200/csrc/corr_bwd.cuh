@@ -29,7 +29,7 @@ template <class Cfg, int SIGN>
 __global__ void __launch_bounds__(Cfg::NT)
 corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
                 const float* __restrict__ X, float* __restrict__ res,
-                int C, int H, int W, int tiles_x, int tiles_y, float slope)
+                int C, int H, int W, int tiles_x, int tiles_y, int cgroup, float slope)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, r = Cfg::r, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, NT = Cfg::NT, HH = Cfg::HH, HWD = Cfg::HWD, HP = Cfg::HP;
@@ -63,22 +63,26 @@ corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
         G[d] = g;
     }
 
+    // output channels are independent: blockIdx.y selects a group of `cgroup` channels, which gives
+    // small images (6x7, 12x14 pyramid levels) enough CTAs to fill the machine
     const float nelems = (float)C;
-    for (int c0 = 0; c0 < C; c0 += CK) {
+    const int c_begin = blockIdx.y * cgroup;
+    const int c_end = min(C, c_begin + cgroup);
+    for (int c0 = c_begin; c0 < c_end; c0 += CK) {
         __syncthreads();
         for (int i = tid; i < CK * HH * HWD; i += NT) {
             const int c = i / (HH * HWD), rem = i - c * (HH * HWD);
             const int hy = rem / HWD, hx = rem - hy * HWD;
             const int yy = y0t - R + hy, xx = x0t - R + hx;
             float v = 0.0f;
-            if (c0 + c < C && yy >= 0 && yy < H && xx >= 0 && xx < W)
+            if (c0 + c < c_end && yy >= 0 && yy < H && xx >= 0 && xx < W)
                 v = __ldg(Xn + (size_t)(c0 + c) * HW + (size_t)yy * W + xx);
             sX[c * (HH * HP) + hy * HP + hx] = v;
         }
         __syncthreads();
         const float* base = sX + (ly + R) * HP + (lx + R);
         for (int c = 0; c < CK; ++c) {
-            if (c0 + c >= C) break;
+            if (c0 + c >= c_end) break;
             float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
             for (int d = 0; d < D * D; d += 3) {

@@ -177,19 +177,21 @@ warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
 }
 
 // Autograd of WarpingLayer.  grad_x must be zeroed beforehand
-// (the ABI entry does it on the same stream).  One thread per (n, y, x): the flow gradient is a
-// plain sum over channels (deterministic), the feature gradient a scatter-add.
+// (the ABI entry does it on the same stream).  One thread per (n, channel group, y, x): the feature
+// gradient is a scatter-add; the flow gradient is a sum over channels -- written directly when there
+// is a single channel group (deterministic), accumulated with atomicAdd into a zeroed buffer otherwise.
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                 const float* __restrict__ flow, float* __restrict__ gx,
-                float* __restrict__ gflow, int B, int C, int H, int W)
+                float* __restrict__ gflow, int B, int C, int H, int W, int cpt, int cgroups)
 {
     const size_t HW = (size_t)H * W;
-    const size_t total = (size_t)B * HW;
+    const size_t total = (size_t)B * HW * cgroups;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const size_t pix = idx % HW;
-    const int n = (int)(idx / HW);
+    const int cg = (int)((idx / HW) % cgroups);
+    const int n = (int)(idx / (HW * cgroups));
     const int yy = (int)(pix / W), xx = (int)(pix % W);
     const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
     const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
@@ -203,7 +205,8 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
         const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
         const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
         const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;
-        for (int c = 0; c < C; ++c) {
+        const int c_end = min(C, (cg + 1) * cpt);
+        for (int c = cg * cpt; c < c_end; ++c) {
             const size_t plane = ((size_t)n * C + c) * HW;
             const float g = __ldg(gout + plane + pix);
             const float* p = x + plane + t.off;
@@ -221,8 +224,14 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
         }
     }
     if (gflow) {
-        gflow[(size_t)n * 2 * HW + pix] = gu;
-        gflow[(size_t)n * 2 * HW + HW + pix] = gv;
+        float* gf = gflow + (size_t)n * 2 * HW + pix;
+        if (cgroups == 1) {
+            gf[0] = gu;
+            gf[HW] = gv;
+        } else if (t.off >= 0) {
+            atomicAdd(gf, gu);
+            atomicAdd(gf + HW, gv);
+        }
     }
 }
 

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "corr_bwd.cuh"
+#include "corr_bwd_tma.cuh"
 #include "generic_kernels.cuh"
 #include "pwc_common.cuh"
 #include "warpcorr_fwd.cuh"
@@ -176,6 +177,10 @@ int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, floa
 {
     if (g.W > 16)
         return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
+    // small images (6x7, 12x14 levels: few CTAs, many channels): deep channel chunks, so that the
+    // serial chunk loop is short and each chunk keeps many gathers in flight
+    if (g.C >= 64)
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, (S2 == 1 ? 28 : 16)>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
     return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
 }
 
@@ -235,8 +240,41 @@ int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long blocks = (long long)tiles_x * tiles_y * g.B;
     if (blocks > 0x7fffffffLL) return fail("grid too large");
-    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, slope);
+    // split the (independent) output channels over blockIdx.y until the grid covers ~2 waves
+    int cgroup = g.C;
+    while (cgroup > Cfg::CK && blocks * pwc::cdiv(g.C, cgroup) < 296) cgroup = pwc::round_up(pwc::cdiv(cgroup, 2), Cfg::CK);
+    const dim3 grid((unsigned)blocks, (unsigned)pwc::cdiv(g.C, cgroup));
+    kern<<<grid, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, cgroup, slope);
     return check_launch("corr_bwd_kernel");
+}
+
+// returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
+template <int S2, int CK, int SIGN>
+int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* res,
+                   const pwc::CorrGeom& g, float slope, cudaStream_t st)
+{
+    using Cfg = pwc::BwdTmaCfg<S2, CK>;
+    CUtensorMap mX;
+    if (!make_nchw_map(&mX, X, g.B, g.C, g.H, g.W, Cfg::WP, Cfg::HH, CK)) return -1;
+    auto kern = pwc::corr_bwd_tma_kernel<Cfg, SIGN>;
+    const size_t smem = Cfg::smem_bytes();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+        configured_dev = dev;
+    }
+    const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
+    const long long ntiles = (long long)tiles_x * tiles_y * g.B;
+    if (ntiles > 0x3fffffffLL) return fail("grid too large");
+    static thread_local int sm_count = 0;
+    if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        sm_count = 148;
+    const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, gout, gate, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, slope);
+    return check_launch("corr_bwd_tma_kernel");
 }
 
 // g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
@@ -247,6 +285,18 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
                     "address gradInput out of range otherwise", g.s1);
     if (fast_path(g)) {
+        if (tma_eligible(f1, second, g1, g) && (((uintptr_t)g2 | (uintptr_t)gout) & 15) == 0) {
+            int r1, r2;
+            if (g.s2 == 1) {
+                r1 = launch_bwd_tma<1, 4, +1>(gout, gate, second, g1, g, slope, st);
+                r2 = r1 > 0 ? launch_bwd_tma<1, 4, -1>(gout, gate, f1, g2, g, slope, st) : r1;
+            } else {
+                r1 = launch_bwd_tma<2, 2, +1>(gout, gate, second, g1, g, slope, st);
+                r2 = r1 > 0 ? launch_bwd_tma<2, 2, -1>(gout, gate, f1, g2, g, slope, st) : r1;
+            }
+            if (r1 == 0 || r2 == 0) return 0;
+            if (r1 > 0 && r2 > 0) return 1;
+        }
         if (g.s2 == 1)
             return launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, st) &&
                    launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, st);
@@ -299,8 +349,15 @@ int pwc_warp_backward(const float* grad_out, const float* x, const float* flow, 
     if (grad_x &&
         cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)B * C * H * W, stream) != cudaSuccess)
         return fail("cudaMemsetAsync(grad_x): %s", cudaGetErrorString(cudaGetLastError()));
-    const size_t total = (size_t)B * H * W;
-    pwc::warp_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, grad_x, grad_flow, B, C, H, W);
+    // channel groups in parallel; the flow gradient is then a sum over groups (atomicAdd on a zeroed buffer)
+    int cpt = C;
+    while (cpt > 8 && (size_t)B * H * W * pwc::cdiv(C, cpt) < (size_t)148 * 2048) cpt = pwc::cdiv(cpt, 2);
+    const int cgroups = pwc::cdiv(C, cpt);
+    if (grad_flow && cgroups > 1 &&
+        cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)
+        return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
+    const size_t total = (size_t)B * H * W * cgroups;
+    pwc::warp_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, grad_x, grad_flow, B, C, H, W, cpt, cgroups);
     return check_launch("warp_bwd_kernel");
 }
 

@@ -147,7 +147,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                 float* wo = interior ? warped_out + ((size_t)n * C + c0) * HW + (size_t)gy * W + gx
                                      : nullptr;
                 if (o.x < 0) {
-#pragma unroll
+#pragma unroll 8
                     for (int c = 0; c < CK; ++c) {
                         dst[c * (HH * HP)] = 0.0f;
                         if (wo && c0 + c < C) wo[(size_t)c * HW] = 0.0f;
@@ -155,7 +155,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                 } else {
                     const int dx = o.y & 1, dyw = o.y >> 1;
                     const float* p00 = f2n + (size_t)c0 * HW + o.x;
-#pragma unroll
+#pragma unroll 8
                     for (int c = 0; c < CK; ++c) {
                         float v = 0.0f;
                         if (c0 + c < C) {
