@@ -487,6 +487,24 @@ def measure_extras(torch, pkg, dev, sets, make_set):
     out["pyramid5_fwd_B32_384x448"] = {"ms": ms, "pairs_per_s": B / (ms * 1e-3), "GBps": pb / ms / 1e6,
                                        "frac": pb / ms / 1e6 / peak}
 
+    # full PWC-Net forward (reference architecture, random init, convs on cuDNN, hot path fused):
+    # the north star's "pairs/s at 448x384" figure; the conv stack is out of scope
+    try:
+        from pwc_net_pytorch_b200.model import Net, default_args
+        net = Net(default_args(device=dev)).eval()
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for Bf in (1, 16):
+                xin = torch.rand(Bf, 3, 2, 384, 448, device=dev) * 255.0
+                with torch.no_grad():
+                    ms = time_cuda(torch, lambda: net(xin), iters=5, warm=2)
+                out[f"full_forward_384x448_B{Bf}_{'tf32' if tf32 else 'fp32'}convs"] = {
+                    "ms": ms, "pairs_per_s": Bf / (ms * 1e-3)}
+        torch.backends.cudnn.allow_tf32 = True
+        del net
+    except Exception as e:
+        out["full_forward_error"] = repr(e)
+
     # GPU reference bar: the reference's own kernels (sm_100a build) + torch grid_sample
     try:
         from oracle import ref_cuda

@@ -143,6 +143,8 @@ def cost_volume_layer_port(src, tgt, search_range=4):
         # out[y, x] = sum_c src[y, x] * tgt[y+dy, x+dx] where both are in range
         ys0, ys1 = max(0, -dy), min(H, H - dy)
         xs0, xs1 = max(0, -dx), min(W, W - dx)
+        if ys1 <= ys0 or xs1 <= xs0:      # shift larger than the image: the slice stays zero
+            continue
         out[:, I, ys0:ys1, xs0:xs1] = (src[:, :, ys0:ys1, xs0:xs1] *
                                        tgt[:, :, ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]).sum(1)
     return out / float(len(order))

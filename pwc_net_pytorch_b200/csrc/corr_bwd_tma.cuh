@@ -143,27 +143,41 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
         // ---- this thread's 8 x 9 output-gradient taps (registers for the whole tile) ----
         float G[PX][D];
         {
+            // 128-bit loads: a strip starts on a multiple of 8 pixels and W % 4 == 0, so every aligned
+            // quad is entirely inside or outside the row.  For SIGN < 0 the 8 wanted values start at
+            // xs - dx; they are picked out of 2 or 3 aligned quads with compile-time indices.
             const int y = tc.y0 + lr, xs = tc.x0 + ls * PX;
             const int dy = (wd - 4) * S2;
-            const float* gon = gout + (size_t)tc.n * (D * D) * HW;
-            const float* gaten = gate ? gate + (size_t)tc.n * (D * D) * HW : nullptr;
+            const int gy = (SIGN > 0) ? y : y - dy;
+            const bool row_ok = (y < H) && gy >= 0 && gy < H;
+            const float* gon = gout + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W;
+            const float* gaten = gate ? gate + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W
+                                      : nullptr;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const int dx = (d - 4) * S2;
-                const int gy = (SIGN > 0) ? y : y - dy;
-                const size_t plane = (size_t)(wd * D + d) * HW;
+                const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
+                const int sh = ((-dx) % 4 + 4) % 4;            // (xs - dx) mod 4, compile time
+                const int xb = xs - dx - sh;                   // aligned start
+                constexpr int NQ = 3;
+                float t[4 * NQ];
 #pragma unroll
-                for (int p = 0; p < PX; ++p) {
-                    const int x = xs + p;
-                    const int gx = (SIGN > 0) ? x : x - dx;
-                    float v = 0.0f;
-                    if (y < H && x < W && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                        const size_t o = plane + (size_t)gy * W + gx;
-                        v = __ldg(gon + o);
-                        if (gaten && __ldg(gaten + o) < 0.0f) v *= slope;   // leaky_relu_ backward, model.py:84
+                for (int q = 0; q < NQ; ++q) {
+                    const int x = xb + 4 * q;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W) {
+                        v = __ldg(reinterpret_cast<const float4*>(gon + (size_t)d * HW + x));
+                        if (gaten) {   // leaky_relu_ backward, model.py:84: gate by the sign of the forward output
+                            const float4 o = __ldg(reinterpret_cast<const float4*>(gaten + (size_t)d * HW + x));
+                            if (o.x < 0.0f) v.x *= slope;
+                            if (o.y < 0.0f) v.y *= slope;
+                            if (o.z < 0.0f) v.z *= slope;
+                            if (o.w < 0.0f) v.w *= slope;
+                        }
                     }
-                    G[p][d] = v;
+                    t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
                 }
+#pragma unroll
+                for (int p = 0; p < PX; ++p) G[p][d] = (xs + p < W) ? t[sh + p] : 0.0f;
             }
         }
 
