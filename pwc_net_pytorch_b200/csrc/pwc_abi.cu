@@ -81,9 +81,27 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long blocks = (long long)tiles_x * tiles_y * g.B;
-    if (blocks > 0x7fffffffLL) return fail("grid too large");
-    kern<<<(unsigned)blocks, Cfg::NT, smem, st>>>(f1, f2, flow, out, warped, g.C, g.H, g.W, tiles_x,
-                                                  tiles_y, act, slope);
+    if (blocks > 0x0fffffffLL) return fail("grid too large");
+    // few tiles but many channels (small pyramid levels): split the channels over a thread-block
+    // cluster of up to 8 CTAs per tile (deterministic DSMEM reduction inside the kernel)
+    int ksplit = 1;
+    while (ksplit < 8 && blocks * ksplit < 148 && g.C / (ksplit * 2) >= 8) ksplit *= 2;
+    const int cper = pwc::cdiv(g.C, ksplit);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(blocks * ksplit));
+    cfg.blockDim = dim3(Cfg::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ksplit;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, f1, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, act, slope,
+                           ksplit, cper) != cudaSuccess)
+        return fail("warpcorr_fwd_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("warpcorr_fwd_kernel");
 }
 

@@ -17,6 +17,8 @@
 // channel chunk the CTA stages the f1 tile and the *warped* f2 tile-plus-halo in shared memory
 // (bilinear taps are computed once per CTA from the flow and reused for every channel).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "pwc_common.cuh"
 
 namespace pwc {
@@ -57,9 +59,11 @@ struct FwdCfg {
     static constexpr int WSPAN = PX + 2 * R;       // warped values one strip needs per row
     static constexpr int W2_ELEMS = CK * HH * HP;
     static constexpr int F1_ELEMS = CK * TH * FP;
+    static constexpr int RED_ELEMS = PX * D * NT;      // split-K staging: one accumulator set per thread
+    static constexpr int W2_ALLOC = W2_ELEMS > RED_ELEMS ? W2_ELEMS : RED_ELEMS;   // the staging aliases the warped tile
     static constexpr size_t smem_bytes(bool has_flow)
     {
-        return sizeof(float) * (size_t)(W2_ELEMS + F1_ELEMS) +
+        return sizeof(float) * (size_t)(W2_ALLOC + F1_ELEMS) +
                (has_flow ? (size_t)NHALO * (sizeof(float4) + sizeof(int2)) : 0);
     }
     static_assert(PX % 4 == 0, "strips are loaded with 128-bit shared loads");
@@ -71,8 +75,12 @@ __global__ void __launch_bounds__(Cfg::NT)
 warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                     const float* __restrict__ flow, float* __restrict__ out,
                     float* __restrict__ warped_out,
-                    int C, int H, int W, int tiles_x, int tiles_y, int act, float slope)
+                    int C, int H, int W, int tiles_x, int tiles_y, int act, float slope, int ksplit, int cper)
 {
+    // ksplit > 1: the kernel is launched in thread-block clusters of ksplit CTAs; the CTAs of a cluster
+    // share one tile and split its channels (cper each); partial accumulators are summed through
+    // distributed shared memory in rank order, so the result stays deterministic.  This is what gives
+    // the 6x7 / 12x14 pyramid levels (few tiles, 128-196 channels) enough CTAs to fill the machine.
     constexpr int D = Cfg::D, S2 = Cfg::S2, PX = Cfg::PX, LW = Cfg::LW, CK = Cfg::CK;
     constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, HWD = Cfg::HWD;
     constexpr int HP = Cfg::HP, FP = Cfg::FP, NT = Cfg::NT, NHALO = Cfg::NHALO;
@@ -80,13 +88,16 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 
     extern __shared__ __align__(16) float smem[];
     float* sW2 = smem;
-    float* sF1 = sW2 + Cfg::W2_ELEMS;
+    float* sF1 = sW2 + Cfg::W2_ALLOC;
     float4* sTapW = reinterpret_cast<float4*>(sF1 + Cfg::F1_ELEMS);
     int2* sTapO = reinterpret_cast<int2*>(sTapW + NHALO);
 
     const int tid = threadIdx.x, lane = tid & 31, wd = tid >> 5;
     const int ls = lane % LW, lr = lane / LW;
-    int t = blockIdx.x;
+    const int rank = (ksplit > 1) ? (int)(blockIdx.x % ksplit) : 0;
+    const int c_begin = rank * cper;
+    const int c_end = min(C, c_begin + cper);
+    int t = blockIdx.x / ksplit;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     const int n = t / tiles_y;
@@ -120,7 +131,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[p][d] = 0.0f;
 
-    for (int c0 = 0; c0 < C; c0 += CK) {
+    for (int c0 = c_begin; c0 < c_end; c0 += CK) {
         __syncthreads();   // previous chunk fully consumed (and taps visible on the first pass)
 
         // ---- stage the f1 tile (zero outside the image / beyond C) ----
@@ -129,7 +140,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
             const int ly = rem / TW, lx = rem - ly * TW;
             const int y = y0t + ly, x = x0t + lx;
             float v = 0.0f;
-            if (c0 + c < C && y < H && x < W) v = __ldg(f1n + (size_t)(c0 + c) * HW + (size_t)y * W + x);
+            if (c0 + c < c_end && y < H && x < W) v = __ldg(f1n + (size_t)(c0 + c) * HW + (size_t)y * W + x);
             sF1[c * (TH * FP) + ly * FP + lx] = v;
         }
 
@@ -150,7 +161,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 #pragma unroll 8
                     for (int c = 0; c < CK; ++c) {
                         dst[c * (HH * HP)] = 0.0f;
-                        if (wo && c0 + c < C) wo[(size_t)c * HW] = 0.0f;
+                        if (wo && c0 + c < c_end) wo[(size_t)c * HW] = 0.0f;
                     }
                 } else {
                     const int dx = o.y & 1, dyw = o.y >> 1;
@@ -158,7 +169,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 #pragma unroll 8
                     for (int c = 0; c < CK; ++c) {
                         float v = 0.0f;
-                        if (c0 + c < C) {
+                        if (c0 + c < c_end) {
                             const float* p = p00 + (size_t)c * HW;
                             const float v00 = __ldg(p), v01 = __ldg(p + dx);
                             const float v10 = __ldg(p + dyw), v11 = __ldg(p + dyw + dx);
@@ -175,7 +186,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                 const int hy = rem / HWD, hx = rem - hy * HWD;
                 const int y = y0t - R + hy, x = x0t - R + hx;
                 float v = 0.0f;
-                if (c0 + c < C && y >= 0 && y < H && x >= 0 && x < W)
+                if (c0 + c < c_end && y >= 0 && y < H && x >= 0 && x < W)
                     v = __ldg(f2n + (size_t)(c0 + c) * HW + (size_t)y * W + x);
                 sW2[c * (HH * HP) + hy * HP + hx] = v;
             }
@@ -203,6 +214,29 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
 #pragma unroll
                 for (int d = 0; d < D; ++d) acc[p][d] = fmaf(f[p], w[p + d * S2], acc[p][d]);
         }
+    }
+
+    if (ksplit > 1) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        __syncthreads();                       // every warp is done reading the warped tile it aliases
+        float* sRed = sW2;
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int d = 0; d < D; ++d) sRed[(p * D + d) * NT + tid] = acc[p][d];
+        cluster.sync();
+        if (rank == 0) {
+            for (int r = 1; r < ksplit; ++r) {
+                const float* remote = cluster.map_shared_rank(sRed, r);
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) acc[p][d] += remote[(p * D + d) * NT + tid];
+            }
+        }
+        cluster.sync();                        // remote shared memory stays valid until rank 0 has read it
+        if (rank != 0) return;
     }
 
     // ---- epilogue: 1/C (correlation_cuda_kernel.cu:65,100), optional LeakyReLU (model.py:84) ----
