@@ -45,7 +45,7 @@ extern "C" {
 typedef struct CUstream_st *cudaStream_t;
 #endif
 
-#define PWC_B200_ABI_VERSION 1
+#define PWC_B200_ABI_VERSION 2
 
 /* ---- legacy launchers: correlation_cuda_kernel.h:5-39 ------------------------------------- */
 int Correlation_forward_cuda_kernel(
@@ -96,6 +96,8 @@ int pwc_warpcorr_forward(const float *f1, const float *f2, const float *flow,
 
 /* ---- backward of pwc_warpcorr_forward.
  * out        : the forward result, read only when act != 0 (sign gate of leaky_relu_).
+ * warped     : optional x2_warp as written by pwc_warpcorr_forward(warped_out) for the same inputs;
+ *              when given, the backward does not re-evaluate the warp (NULL: it does).
  * workspace  : device scratch of pwc_warpcorr_backward_workspace(...) bytes (may be NULL if 0).
  * grad_f1, grad_f2 : [B,C,H,W]; grad_flow: [B,2,H,W] (NULL allowed iff flow == NULL).
  * stride1 must be 1. ------------------------------------------------------------------------- */
@@ -103,7 +105,7 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
                                           int pad_size, int kernel_size, int max_displacement,
                                           int stride1, int stride2);
 int pwc_warpcorr_backward(const float *grad_out, const float *f1, const float *f2,
-                          const float *flow, const float *out,
+                          const float *flow, const float *out, const float *warped,
                           float *grad_f1, float *grad_f2, float *grad_flow,
                           void *workspace, long long workspace_bytes,
                           int B, int C, int H, int W,

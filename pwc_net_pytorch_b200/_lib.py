@@ -58,7 +58,7 @@ def _declare(L):
     L.pwc_warpcorr_forward.restype = _int
     L.pwc_warpcorr_backward_workspace.argtypes = [_int] * 10
     L.pwc_warpcorr_backward_workspace.restype = ctypes.c_longlong
-    L.pwc_warpcorr_backward.argtypes = ([_c_float_p] * 8 + [ctypes.c_void_p, ctypes.c_longlong] +
+    L.pwc_warpcorr_backward.argtypes = ([_c_float_p] * 9 + [ctypes.c_void_p, ctypes.c_longlong] +
                                         [_int] * 9 + [_int, ctypes.c_float] + [_stream])
     L.pwc_warpcorr_backward.restype = _int
     L.pwc_last_error.argtypes = []
@@ -86,7 +86,7 @@ def load():
                     "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
             L = ctypes.CDLL(LIB_PATH)
             _declare(L)
-            if L.pwc_abi_version() != 1:
+            if L.pwc_abi_version() != 2:
                 raise RuntimeError("libpwc_b200.so ABI version mismatch; rebuild it")
             _lib = L
     return _lib

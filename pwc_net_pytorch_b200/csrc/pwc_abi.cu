@@ -399,7 +399,7 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
 }
 
 int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
-                          const float* flow, const float* out, float* grad_f1, float* grad_f2,
+                          const float* flow, const float* out, const float* warped_in, float* grad_f1, float* grad_f2,
                           float* grad_flow, void* workspace, long long workspace_bytes, int B,
                           int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
                           int stride1, int stride2, int act, float slope, cudaStream_t stream)
@@ -416,9 +416,13 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     if (!workspace || workspace_bytes < need)
         return fail("pwc_warpcorr_backward: workspace of %lld bytes required, got %lld", need, workspace_bytes);
     const size_t N = (size_t)B * C * H * W;
-    float* warped = static_cast<float*>(workspace);
-    float* gwarped = warped + N;
-    if (!pwc_warp_forward(f2, flow, warped, B, C, H, W, stream)) return 0;
+    float* wbuf = static_cast<float*>(workspace);
+    float* gwarped = wbuf + N;
+    const float* warped = warped_in;
+    if (!warped) {      // re-materialise x2_warp (the forward never stored it)
+        if (!pwc_warp_forward(f2, flow, wbuf, B, C, H, W, stream)) return 0;
+        warped = wbuf;
+    }
     if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream)) return 0;
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
 }

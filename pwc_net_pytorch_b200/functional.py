@@ -153,6 +153,10 @@ class WarpCorrelationFunction(Function):
         flow = None if flow is None else flow.contiguous()
         oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
         out = torch.empty((B, oc, oh, ow), dtype=torch.float32, device=dev)
+        # If the caller asks for x2_warp anyway (model.py:107,113) and a backward will follow, the exported
+        # tensor is handed to the backward, which then skips re-evaluating the warp.  It is not exported
+        # just for that: measured on B200 the export costs the forward about as much as it saves.
+        needs_grad = want_warped and flow is not None and any(ctx.needs_input_grad[:3])
         warped = torch.empty_like(x2) if want_warped else None
         with torch.cuda.device(dev):
             ok = _lib.load().pwc_warpcorr_forward(
@@ -165,7 +169,7 @@ class WarpCorrelationFunction(Function):
         if flow is None:
             ctx.save_for_backward(x1, x2, out if act else None)
         else:
-            ctx.save_for_backward(x1, x2, out if act else None, flow)
+            ctx.save_for_backward(x1, x2, out if act else None, flow, warped if needs_grad else None)
         if want_warped:
             ctx.mark_non_differentiable(warped)
             return out, warped
@@ -175,10 +179,10 @@ class WarpCorrelationFunction(Function):
     def backward(ctx, grad_out, *unused):
         pad_size, kernel_size, max_displacement, stride1, stride2, act, slope = ctx.params
         if ctx.has_flow:
-            x1, x2, out, flow = ctx.saved_tensors
+            x1, x2, out, flow, warped = ctx.saved_tensors
         else:
             x1, x2, out = ctx.saved_tensors
-            flow = None
+            flow = warped = None
         grad_out = grad_out.contiguous()
         _check_inputs(grad_out)
         B, C, H, W = x1.shape
@@ -191,7 +195,7 @@ class WarpCorrelationFunction(Function):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x1.device) if ws_bytes else None
         with torch.cuda.device(x1.device):
             ok = L.pwc_warpcorr_backward(
-                _ptr(grad_out), _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(g1), _ptr(g2),
+                _ptr(grad_out), _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(warped), _ptr(g1), _ptr(g2),
                 _ptr(gflow), _ptr(ws), ws_bytes, B, C, H, W,
                 pad_size, kernel_size, max_displacement, stride1, stride2,
                 int(act), float(slope), _stream())
