@@ -27,7 +27,7 @@ __device__ __forceinline__ float second_operand(const float* __restrict__ f2n,
     if (flown == nullptr) return __ldg(plane + (size_t)y * g.W + x);
     const float u = __ldg(flown + (size_t)y * g.W + x);
     const float v = __ldg(flown + HW + (size_t)y * g.W + x);
-    const Tap t = make_tap((float)x + u, (float)y + v, g.H, g.W);
+    const Tap t = make_tap(x, y, u, v, g.H, g.W);
     return t.off < 0 ? 0.0f : tap_sample(t, plane);
 }
 
@@ -164,7 +164,7 @@ warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow,
     const int yy = (int)(pix / W), xx = (int)(pix % W);
     const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
     const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
-    const Tap t = make_tap((float)xx + u, (float)yy + v, H, W);
+    const Tap t = make_tap(xx, yy, u, v, H, W);
     const int c0 = cg * CPT;
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
@@ -195,13 +195,12 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
     const int yy = (int)(pix / W), xx = (int)(pix % W);
     const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
     const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
-    const float sx = (float)xx + u, sy = (float)yy + v;
-    const Tap t = make_tap(sx, sy, H, W);
+    float ax = 0.0f, ay = 0.0f;
+    int x0 = 0, y0 = 0;
+    const Tap t = make_tap(xx, yy, u, v, H, W, &ax, &ay, &x0, &y0);
     float gu = 0.0f, gv = 0.0f;
     if (t.off >= 0) {
-        const float ax = sx - floorf(sx), ay = sy - floorf(sy);
         // corners outside the image read as 0 (their clamped addresses are masked out)
-        const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
         const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
         const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
         const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;

@@ -18,26 +18,33 @@ struct Tap {
     int dyw;    // 0 or W
 };
 
-// Sample position (sx, sy) in source-pixel units -> tap.  This is F.grid_sample(bilinear, zeros,
-// align_corners=True) at the un-normalised coordinate, which is what modules.py:36-41 evaluates
-// under torch 0.4.0: out = sum over the 4 corners of w * x[corner],
-// corners outside [0,W)x[0,H) contribute 0.
-__device__ __forceinline__ Tap make_tap(float sx, float sy, int H, int W)
+// Pixel (x, y) displaced by the flow (u, v) -> tap.  This is F.grid_sample(bilinear, zeros,
+// align_corners=True) at the un-normalised coordinate (x+u, y+v), which is what modules.py:36-41
+// evaluates under torch 0.4.0: out = sum over the 4 corners of
+// w * x[corner], corners outside [0,W)x[0,H) contribute 0.
+// The flow is split into floor + fraction *before* the pixel coordinate is added: u - floor(u) is
+// exact in fp32, so the bilinear weights carry no rounding from the image width (the reference's own
+// normalise/denormalise round trip costs ~W * 2^-24 px).
+// ax/ay (optional) receive the fractions, x0/y0 the top-left corner.
+__device__ __forceinline__ Tap make_tap(int x, int y, float u, float v, int H, int W,
+                                        float* ax_out = nullptr, float* ay_out = nullptr,
+                                        int* x0_out = nullptr, int* y0_out = nullptr)
 {
     Tap t;
-    // Rejects NaN/Inf and anything whose 4 corners are all outside (also keeps the int
-    // conversion below well defined).
-    const bool live = (sx > -1.0f) && (sx < (float)W) && (sy > -1.0f) && (sy < (float)H);
-    if (!live) {
-        t.w00 = t.w01 = t.w10 = t.w11 = 0.0f;
-        t.off = -1; t.dx = 0; t.dyw = 0;
-        return t;
-    }
-    const float fx = floorf(sx), fy = floorf(sy);
-    const float ax = sx - fx, ay = sy - fy;
-    const int x0 = (int)fx, y0 = (int)fy;
+    t.w00 = t.w01 = t.w10 = t.w11 = 0.0f;
+    t.off = -1; t.dx = 0; t.dyw = 0;
+    // rejects NaN / Inf / absurd displacements (also keeps the int conversions well defined)
+    if (!(fabsf(u) < 1.0e6f) || !(fabsf(v) < 1.0e6f)) return t;
+    const float fu = floorf(u), fv = floorf(v);
+    const float ax = u - fu, ay = v - fv;
+    const int x0 = x + (int)fu, y0 = y + (int)fv;
+    if (ax_out) *ax_out = ax;
+    if (ay_out) *ay_out = ay;
+    if (x0_out) *x0_out = x0;
+    if (y0_out) *y0_out = y0;
+    if (x0 < -1 || x0 >= W || y0 < -1 || y0 >= H) return t;      // all four corners outside
     const int x1 = x0 + 1, y1 = y0 + 1;
-    const bool inx0 = (x0 >= 0), inx1 = (x1 < W);   // x0 < W and x1 >= 0 are implied by `live`
+    const bool inx0 = (x0 >= 0), inx1 = (x1 < W);
     const bool iny0 = (y0 >= 0), iny1 = (y1 < H);
     const float bx = 1.0f - ax, by = 1.0f - ay;
     t.w00 = (inx0 && iny0) ? bx * by : 0.0f;

@@ -116,7 +116,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
             if (y >= 0 && y < H && x >= 0 && x < W) {
                 const float u = __ldg(un + (size_t)y * W + x);
                 const float v = __ldg(un + HW + (size_t)y * W + x);
-                const Tap tp = make_tap((float)x + u, (float)y + v, H, W);
+                const Tap tp = make_tap(x, y, u, v, H, W);
                 w = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
                 o = make_int2(tp.off, (tp.dyw << 1) | tp.dx);
             }

@@ -312,15 +312,18 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                     int meta = TAP_EMPTY;
                     if (y >= 0 && y < H && x >= 0 && x < W) {
-                        const float sx = (float)x + sfl[i], sy = (float)y + sfl[NHALO + i];
-                        if (sx > -1.0f && sx < (float)W && sy > -1.0f && sy < (float)H) {
-                            const float fx = floorf(sx), fy = floorf(sy);
-                            const float ax = sx - fx, ay = sy - fy;
-                            const int x0 = (int)fx, y0 = (int)fy;
-                            w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
-                            meta = ((y0 + 1) << 16) | (x0 + 1);   // x0, y0 >= -1; H, W < 32760 (host check)
-                            mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
-                            mny = min(mny, y0); mxy = max(mxy, y0 + 1);
+                        const float u = sfl[i], v = sfl[NHALO + i];
+                        if (fabsf(u) < 1.0e6f && fabsf(v) < 1.0e6f) {          // rejects NaN / Inf as well
+                            // floor + fraction of the flow first: the fraction is exact in fp32 (pwc_common.cuh)
+                            const float fu = floorf(u), fv = floorf(v);
+                            const float ax = u - fu, ay = v - fv;
+                            const int x0 = x + (int)fu, y0 = y + (int)fv;
+                            if (x0 >= -1 && x0 < W && y0 >= -1 && y0 < H) {
+                                w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
+                                meta = ((y0 + 1) << 16) | (x0 + 1);   // x0, y0 >= -1; H, W < 32760 (host check)
+                                mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
+                                mny = min(mny, y0); mxy = max(mxy, y0 + 1);
+                            }
                         }
                     }
                     tapW[i] = w;
@@ -412,8 +415,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                         const int i = btid + j * NBIL;
                         const int hy = i / HWD, hx = i - hy * HWD;
                         const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
-                        const Tap tp = make_tap((float)x + __ldg(un + (size_t)y * W + x),
-                                                (float)y + __ldg(un + HW + (size_t)y * W + x), H, W);
+                        const Tap tp = make_tap(x, y, __ldg(un + (size_t)y * W + x), __ldg(un + HW + (size_t)y * W + x), H, W);
 #pragma unroll
                         for (int c = 0; c < CK; ++c)
                             v[j][c] = (c0 + c < C && tp.off >= 0)

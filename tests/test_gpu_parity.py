@@ -314,6 +314,64 @@ def test_full_size_properties():
         assert max_rel(o1[sel].cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 112, 256), (1, 32, 96, 320), (2, 64, 56, 128), (1, 16, 50, 52), (3, 5, 17, 36),
+                                   (1, 40, 16, 16), (1, 9, 8, 24)])
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_highres_and_ragged_shapes_fwd_bwd(shape, cfg):
+    """BASELINE.json config 5 level-2 shapes (Sintel 1024x448 -> 112x256, KITTI 1280x384 -> 96x320) and
+    sizes that are not multiples of the 16x16 tile (TMA path, W % 4 == 0) -- forward and all gradients."""
+    B, C, H, W = shape
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=61, flow_sigma=2.5)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    a, b, f, g = to_dev(f1, f2, flow, go)
+    for t in (a, b, f):
+        t.requires_grad_()
+    out = pkg.FusedWarpCorrelation(*cfg)(a, b, f)
+    out.backward(g)
+    ref = co.warpcorr_forward(f1, f2, flow, *cfg)
+    g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, None, *cfg)
+    assert max_rel(out.detach().cpu().numpy(), ref) < TOL
+    assert max_rel(a.grad.cpu().numpy(), g1) < TOL
+    assert max_rel(b.grad.cpu().numpy(), g2) < TOL
+    assert max_rel(f.grad.cpu().numpy(), gf) < TOL
+
+
+def test_backward_with_exported_warp_equals_recomputed_warp():
+    """ABI v2: the backward may consume the x2_warp exported by the forward instead of re-evaluating it."""
+    f1, f2, flow, rng = make_inputs(2, 24, 32, 48, seed=67)
+    go = rng.standard_normal((2, 81, 32, 48)).astype(np.float32)
+    grads = []
+    for export in (False, True):
+        a, b, f, g = to_dev(f1, f2, flow, go)
+        for t in (a, b, f):
+            t.requires_grad_()
+        res = pkg.FusedWarpCorrelation(*REF_CFG, return_warped=export)(a, b, f)
+        (res[0] if export else res).backward(g)
+        grads.append([t.grad.clone() for t in (a, b, f)])
+    for x, y in zip(*grads):
+        assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 2e-6
+
+
+def test_tma_backward_equals_plain_tiled_backward():
+    f1, f2, flow, rng = make_inputs(2, 20, 40, 44, seed=71)
+    go = rng.standard_normal((2, 81, 40, 44)).astype(np.float32)
+    L = _lib.load()
+    grads = []
+    for disable in (0, 1):
+        prev = L.pwc_set_disable_tma(disable)
+        try:
+            a, b, f, g = to_dev(f1, f2, flow, go)
+            for t in (a, b, f):
+                t.requires_grad_()
+            out = pkg.FusedWarpCorrelation(*CANON_CFG, activation=True)(a, b, f)
+            out.backward(g)
+            grads.append([t.grad.clone() for t in (a, b, f)])
+        finally:
+            L.pwc_set_disable_tma(prev)
+    for x, y in zip(*grads):
+        assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 5e-6
+
+
 def test_cuda_graph_capture_and_stream():
     """The entry points enqueue on the caller's current stream and are graph-capturable
     (no allocation, no sync inside the library)."""
