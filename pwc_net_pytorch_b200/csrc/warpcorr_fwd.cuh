@@ -244,7 +244,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
     if (y < H) {
         const float nelems = (float)C;
         const int xs = x0t + ls * PX;
-        const bool vec = ((W & 3) == 0) && (xs + PX <= W);
+        const bool vec = ((W & 3) == 0) && (xs + PX <= W) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             float* o = out + (((size_t)n * (D * D) + (wd * D + d)) * H + y) * W + xs;

@@ -25,6 +25,9 @@ else:
     flow = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).contiguous()
 gout = torch.randn(B, 81, H, W, device=dev)
 op = pkg.FusedWarpCorrelation() if cfgname == "canon" else pkg.FusedWarpCorrelation.from_search_range(4)
+if os.environ.get("PWC_FORCE_GENERIC"):
+    from pwc_net_pytorch_b200 import _lib
+    _lib.load().pwc_set_force_generic(1)
 if what != "fwd":
     f1.requires_grad_(); f2.requires_grad_(); flow.requires_grad_()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

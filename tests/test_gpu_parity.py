@@ -372,6 +372,46 @@ def test_tma_backward_equals_plain_tiled_backward():
         assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 5e-6
 
 
+def test_unaligned_buffers_through_the_c_abi():
+    """Pointers that are only 4-byte aligned (views with a storage offset) must take the non-TMA kernels
+    and still be exact: the C ABI promises nothing about alignment beyond float."""
+    import ctypes
+    f1, f2, flow, rng = make_inputs(2, 6, 16, 24, seed=73)
+    go = rng.standard_normal((2, 81, 16, 24)).astype(np.float32)
+    L = _lib.load()
+
+    def shifted(a):      # device copy living at base + 4 bytes
+        t = torch.from_numpy(a).to(dev())
+        buf = torch.empty(t.numel() + 1, device=dev())
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        return v
+
+    a, b, f, g = (shifted(x) for x in (f1, f2, flow, go))
+    out = shifted(np.zeros((2, 81, 16, 24), np.float32))
+    g1, g2, gf = (shifted(np.zeros_like(x)) for x in (f1, f2, flow))
+    ws = torch.empty(2 * f1.size + 1, device=dev())[1:]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert all(t.data_ptr() % 16 == 4 for t in (a, b, f, g, out, g1, g2, gf))
+    assert L.pwc_warpcorr_forward(p(a), p(b), p(f), p(out), None, 2, 6, 16, 24, 4, 1, 4, 1, 1, 0, 0.0, st)
+    assert L.pwc_warpcorr_backward(p(g), p(a), p(b), p(f), None, None, p(g1), p(g2), p(gf), p(ws), ws.numel() * 4,
+                                   2, 6, 16, 24, 4, 1, 4, 1, 1, 0, 0.0, st)
+    torch.cuda.synchronize()
+    ref = co.warpcorr_forward(f1, f2, flow, *CANON_CFG)
+    r1, r2, rf = co.warpcorr_backward(go, f1, f2, flow, None, *CANON_CFG)
+    assert max_rel(out.cpu().numpy(), ref) < TOL
+    assert max_rel(g1.cpu().numpy(), r1) < TOL
+    assert max_rel(g2.cpu().numpy(), r2) < TOL
+    assert max_rel(gf.cpu().numpy(), rf) < TOL
+    # bad arguments are refused with a message, not a crash
+    assert not L.pwc_warpcorr_forward(None, p(b), p(f), p(out), None, 2, 6, 16, 24, 4, 1, 4, 1, 1, 0, 0.0, st)
+    assert b"null pointer" in L.pwc_last_error()
+    assert not L.pwc_warpcorr_backward(p(g), p(a), p(b), p(f), None, None, p(g1), p(g2), p(gf), None, 0,
+                                       2, 6, 16, 24, 4, 1, 4, 1, 1, 0, 0.0, st)
+    assert b"workspace" in L.pwc_last_error()
+
+
 def test_cuda_graph_capture_and_stream():
     """The entry points enqueue on the caller's current stream and are graph-capturable
     (no allocation, no sync inside the library)."""
