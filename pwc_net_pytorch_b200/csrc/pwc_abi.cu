@@ -326,6 +326,25 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
     return check_launch("corr_bwd_generic_kernel");
 }
 
+// Feature-gradient scatter through the 4-channel-interleaved scratch (see warp_bwd_v4_kernel).
+// scratch holds B * ceil(C/4) * H * W * 4 floats, 16-byte aligned.
+int warp_backward_v4(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
+                     float* scratch, int B, int C, int H, int W, cudaStream_t stream)
+{
+    const int cquads = pwc::cdiv(C, 4);
+    const size_t n4 = (size_t)B * cquads * H * W * 4;
+    if (cudaMemsetAsync(scratch, 0, sizeof(float) * n4, stream) != cudaSuccess)
+        return fail("cudaMemsetAsync(scratch): %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)
+        return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
+    const size_t total = (size_t)B * H * W * cquads;
+    pwc::warp_bwd_v4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow,
+                                                                                B, C, H, W, cquads);
+    if (!check_launch("warp_bwd_v4_kernel")) return 0;
+    pwc::deinterleave4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cquads);
+    return check_launch("deinterleave4_kernel");
+}
+
 }  // namespace
 
 extern "C" {
@@ -394,8 +413,8 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
                                           int, int)
 {
     if (!has_flow) return 0;
-    // warped second operand + its gradient
-    return 2LL * (long long)sizeof(float) * B * C * H * W;
+    // warped second operand + its gradient + the 4-channel-interleaved scatter scratch
+    return (long long)sizeof(float) * (2LL * B * C * H * W + 4LL * B * ((C + 3) / 4) * H * W);
 }
 
 int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
@@ -424,6 +443,9 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
         warped = wbuf;
     }
     if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream)) return 0;
+    float* scratch = gwarped + N;
+    if ((reinterpret_cast<uintptr_t>(scratch) & 15) == 0)
+        return warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, B, C, H, W, stream);
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
 }
 
