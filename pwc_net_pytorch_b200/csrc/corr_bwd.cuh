@@ -7,7 +7,7 @@
 //   g2[n,c,y,x] = 1/C * sum_d gO[n,d,y-dy,x-dx]       * X1[n,c,y-dy,x-dx]      (SIGN = -1)
 //   (dx,dy) = ((d%D - r)*S2, (d/D - r)*S2); terms whose pixel falls outside the image are 0.
 //
-// One thread per pixel of an 8x32 tile keeps its D*D gradient taps G[d] in registers (read once,
+// One thread per pixel of a tile (8x32, or 16x16 / 8x8 for small images) keeps its D*D gradient taps G[d] in registers (read once,
 // coalesced); per channel chunk the CTA stages the tile+halo of the other operand in shared
 // memory and every thread reduces over the D*D displacements for each channel.
 #pragma once
@@ -15,11 +15,13 @@
 
 namespace pwc {
 
-template <int D_, int S2_, int CK_>
+template <int D_, int S2_, int CK_, int TW_ = 32, int TH_ = 8>
 struct BwdCfg {
     static constexpr int D = D_, S2 = S2_, CK = CK_;
     static constexpr int r = (D - 1) / 2, R = r * S2;
-    static constexpr int TW = 32, TH = 8, NT = TW * TH;
+    // one thread per tile pixel; small tiles (8x8, 16x16) keep the 6x7 / 12x14 pyramid levels from
+    // running mostly-idle 256-thread CTAs
+    static constexpr int TW = TW_, TH = TH_, NT = TW * TH;
     static constexpr int HH = TH + 2 * R, HWD = TW + 2 * R;
     static constexpr int HP = HWD | 1;   // odd pitch: rows of a warp never collide
     static constexpr size_t smem_bytes() { return sizeof(float) * (size_t)CK * HH * HP; }

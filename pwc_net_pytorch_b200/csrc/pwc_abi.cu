@@ -240,11 +240,11 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
     return 1;
 }
 
-template <int S2, int SIGN>
-int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float* res,
-                     const pwc::CorrGeom& g, float slope, cudaStream_t st)
+template <int S2, int SIGN, int TW = 32, int TH = 8>
+int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, float* res,
+                         const pwc::CorrGeom& g, float slope, cudaStream_t st)
 {
-    using Cfg = pwc::BwdCfg<9, S2, 16>;
+    using Cfg = pwc::BwdCfg<9, S2, 16, TW, TH>;
     auto kern = pwc::corr_bwd_kernel<Cfg, SIGN>;
     const size_t smem = Cfg::smem_bytes();
     static thread_local int configured_dev = -1;
@@ -293,6 +293,15 @@ int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* 
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     kern<<<grid, Cfg::NT, smem, st>>>(mX, gout, gate, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, slope);
     return check_launch("corr_bwd_tma_kernel");
+}
+
+template <int S2, int SIGN>
+int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float* res,
+                     const pwc::CorrGeom& g, float slope, cudaStream_t st)
+{
+    if (g.W <= 8 && g.H <= 8) return launch_bwd_tiled_cfg<S2, SIGN, 8, 8>(gout, gate, X, res, g, slope, st);
+    if (g.W <= 16) return launch_bwd_tiled_cfg<S2, SIGN, 16, 16>(gout, gate, X, res, g, slope, st);
+    return launch_bwd_tiled_cfg<S2, SIGN, 32, 8>(gout, gate, X, res, g, slope, st);
 }
 
 // g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
