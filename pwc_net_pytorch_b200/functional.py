@@ -19,6 +19,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager is a
+    measurable part of the launch overhead of the small pyramid levels)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -39,13 +58,22 @@ def _check_inputs(*tensors):
     return dev
 
 
+_shape_cache = {}
+
+
 def corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
-    """correlation_cuda.c:20-34."""
+    """correlation_cuda.c:20-34 (answered by the library, memoised: it is on every call's path)."""
+    key = (H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+    hit = _shape_cache.get(key)
+    if hit is not None:
+        return hit
     oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     ok = _lib.load().pwc_corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1,
                                            stride2, ctypes.byref(oc), ctypes.byref(oh),
                                            ctypes.byref(ow))
     _lib.check(ok, "pwc_corr_output_shape")
+    if len(_shape_cache) < 4096:
+        _shape_cache[key] = (oc.value, oh.value, ow.value)
     return oc.value, oh.value, ow.value
 
 
@@ -71,7 +99,7 @@ class CorrelationFunction(Function):
         oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
         output = torch.empty((B, oc, oh, ow), dtype=torch.float32, device=dev)
         L = _lib.load()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ok = L.Correlation_forward_cuda_kernel(
                 _ptr(output), B, oc, oh, ow, *_dense_strides(output),
                 _ptr(input1), C, H, W, *_dense_strides(input1),
@@ -91,7 +119,7 @@ class CorrelationFunction(Function):
         grad_input1 = torch.empty_like(input1)
         grad_input2 = torch.empty_like(input2)
         L = _lib.load()
-        with torch.cuda.device(input1.device):
+        with _on_device(input1.device):
             ok = L.Correlation_backward_cuda_kernel(
                 _ptr(grad_output), *grad_output.shape, *_dense_strides(grad_output),
                 _ptr(input1), C, H, W, *_dense_strides(input1),
@@ -116,7 +144,7 @@ class WarpFunction(Function):
         ctx.save_for_backward(x, flow)
         out = torch.empty_like(x)
         B, C, H, W = x.shape
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ok = _lib.load().pwc_warp_forward(_ptr(x), _ptr(flow), _ptr(out), B, C, H, W, _stream())
         _lib.check(ok, "pwc_warp_forward")
         return out
@@ -129,7 +157,7 @@ class WarpFunction(Function):
         B, C, H, W = x.shape
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             ok = _lib.load().pwc_warp_backward(_ptr(grad_out), _ptr(x), _ptr(flow), _ptr(gx),
                                                _ptr(gflow), B, C, H, W, _stream())
         _lib.check(ok, "pwc_warp_backward")
@@ -158,7 +186,7 @@ class WarpCorrelationFunction(Function):
         # just for that: measured on B200 the export costs the forward about as much as it saves.
         needs_grad = want_warped and flow is not None and any(ctx.needs_input_grad[:3])
         warped = torch.empty_like(x2) if want_warped else None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ok = _lib.load().pwc_warpcorr_forward(
                 _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(warped), B, C, H, W,
                 pad_size, kernel_size, max_displacement, stride1, stride2,
@@ -193,7 +221,7 @@ class WarpCorrelationFunction(Function):
         ws_bytes = int(L.pwc_warpcorr_backward_workspace(B, C, H, W, int(flow is not None), pad_size,
                                                          kernel_size, max_displacement, stride1, stride2))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x1.device) if ws_bytes else None
-        with torch.cuda.device(x1.device):
+        with _on_device(x1.device):
             ok = L.pwc_warpcorr_backward(
                 _ptr(grad_out), _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), _ptr(warped), _ptr(g1), _ptr(g2),
                 _ptr(gflow), _ptr(ws), ws_bytes, B, C, H, W,
