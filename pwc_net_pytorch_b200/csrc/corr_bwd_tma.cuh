@@ -22,6 +22,15 @@
 
 namespace pwc {
 
+// TMA prefetch of a 4-D box into L2 (no shared memory involved): used to pull the next tile's
+// output-gradient taps towards the SM while the current tile is being processed.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int x, int y, int c, int n)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(x), "r"(y),
+                 "r"(c), "r"(n)
+                 : "memory");
+}
+
 template <int S2_, int CK_>
 struct BwdTmaCfg {
     static constexpr int D = 9, S2 = S2_, CK = CK_, PX = 8;
@@ -39,6 +48,7 @@ struct BwdTmaCfg {
     static constexpr int PART_ELEMS = D * SLICE_ELEMS;
     static constexpr uint32_t X_BYTES = X_ELEMS * 4;
     static constexpr int CTRL_BYTES = 128;
+    static constexpr int GBOX_C = 27;                       // gradient-tap prefetch box: 27 of the 81 channels
     static_assert(WP % 8 == 4 && PP % 8 == 4, "pitches must be 4 mod 8 floats");
     static_assert(X_BYTES % 128 == 0 && (PART_ELEMS * 4) % 128 == 0, "buffers stay 128B aligned");
     static_assert((2 * NS + 4) * 8 <= CTRL_BYTES, "control block too small");
@@ -47,7 +57,8 @@ struct BwdTmaCfg {
 
 template <class Cfg, int SIGN>
 __global__ void __launch_bounds__(Cfg::NT, 1)
-corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ gout,
+corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                    const float* __restrict__ gout,
                     const float* __restrict__ gate, float* __restrict__ res,
                     int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float slope)
 {
@@ -88,9 +99,19 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
         // ================================ T: TMA issue ================================
         if (tid != NCONS + NRED) return;
         prefetch_tmap(&tmX);
+        prefetch_tmap(&tmG);
         for (int g = 0; g < total; ++g) {
             const int s = g % NS;
             const TileCoord tc = tile_coord(blockIdx.x + (g / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
+            if (g % nchunks == 0 && g / nchunks + 1 < my_tiles) {
+                // first chunk of a tile: pull the NEXT tile's output-gradient taps into L2, so that the
+                // consumers' per-tile tap loads (their only global loads) hit L2 instead of DRAM
+                const TileCoord tn = tile_coord(blockIdx.x + (g / nchunks + 1) * gridDim.x, tiles_x, tiles_y, TH, TW);
+                const int off = (SIGN > 0) ? 0 : R;
+#pragma unroll
+                for (int j = 0; j < (D * D) / Cfg::GBOX_C; ++j)
+                    tma_prefetch_4d(&tmG, tn.x0 - off, tn.y0 - off, j * Cfg::GBOX_C, tn.n);
+            }
             if (g >= NS) mbar_wait(&barEmpty[s], ((g / NS) - 1) & 1);
             mbar_expect_tx(&barFull[s], Cfg::X_BYTES);
             tma_load_4d(sX + s * Cfg::X_ELEMS, &tmX, &barFull[s], tc.x0 - R, tc.y0 - R, (g % nchunks) * CK, tc.n);

@@ -272,8 +272,12 @@ int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* 
                    const pwc::CorrGeom& g, float slope, cudaStream_t st)
 {
     using Cfg = pwc::BwdTmaCfg<S2, CK>;
-    CUtensorMap mX;
+    CUtensorMap mX, mG;
     if (!make_nchw_map(&mX, X, g.B, g.C, g.H, g.W, Cfg::WP, Cfg::HH, CK)) return -1;
+    // output-gradient prefetch box: the tile (g1) or the tile + halo (gradient w.r.t. the second operand)
+    if (!make_nchw_map(&mG, gout, g.B, 81, g.H, g.W, SIGN > 0 ? Cfg::TW : Cfg::HWD, SIGN > 0 ? Cfg::TH : Cfg::HH,
+                       Cfg::GBOX_C))
+        return -1;
     auto kern = pwc::corr_bwd_tma_kernel<Cfg, SIGN>;
     const size_t smem = Cfg::smem_bytes();
     static thread_local int configured_dev = -1;
@@ -291,7 +295,7 @@ int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* 
     if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         sm_count = 148;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
-    kern<<<grid, Cfg::NT, smem, st>>>(mX, gout, gate, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, slope);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, gate, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, slope);
     return check_launch("corr_bwd_tma_kernel");
 }
 
