@@ -587,6 +587,14 @@ def measure_extras(torch, pkg, dev, sets, make_set):
                 out[f"full_forward_384x448_B{Bf}_{'tf32' if tf32 else 'fp32'}convs"] = {
                     "ms": ms, "pairs_per_s": Bf / (ms * 1e-3)}
         torch.backends.cudnn.allow_tf32 = True
+        # whole forward replayed from one CUDA graph (row f: the coarse levels are launch latency)
+        from pwc_net_pytorch_b200.graphed import GraphedForward
+        for Bf in (1, 16):
+            xin = torch.rand(Bf, 3, 2, 384, 448, device=dev) * 255.0
+            gf = GraphedForward(net, xin)
+            ms = time_cuda(torch, lambda: gf(xin), iters=10, warm=2)
+            out[f"full_forward_384x448_B{Bf}_tf32convs_cudagraph"] = {"ms": ms, "pairs_per_s": Bf / (ms * 1e-3)}
+            del gf
         del net
     except Exception as e:
         out["full_forward_error"] = repr(e)

@@ -94,6 +94,17 @@ int pwc_warpcorr_forward(const float *f1, const float *f2, const float *flow,
                          int stride1, int stride2,
                          int act, float slope, cudaStream_t stream);
 
+/* ---- same, writing into a larger buffer: image n's [D*D, oh, ow] block starts at
+ * out + n * out_batch_stride (floats; >= D*D*oh*ow, 0 means dense).  This is how the cost volume is
+ * written straight into the flow estimator's concatenated input [x1 | corr | flow] (model.py:89-91)
+ * instead of being copied there by torch.cat. ------------------------------------------------- */
+int pwc_warpcorr_forward_strided(const float *f1, const float *f2, const float *flow,
+                                 float *out, long long out_batch_stride, float *warped_out,
+                                 int B, int C, int H, int W,
+                                 int pad_size, int kernel_size, int max_displacement,
+                                 int stride1, int stride2,
+                                 int act, float slope, cudaStream_t stream);
+
 /* ---- backward of pwc_warpcorr_forward.
  * out        : the forward result, read only when act != 0 (sign gate of leaky_relu_).
  * warped     : optional x2_warp as written by pwc_warpcorr_forward(warped_out) for the same inputs;

@@ -19,6 +19,7 @@ from .modules import FusedWarpCorrelation, WarpingLayer
 
 __all__ = ["Correlation", "CorrelationFunction", "WarpingLayer", "FusedWarpCorrelation",
            "functional", "install_as_reference_modules"]
+# model.Net / graphed.GraphedForward are imported on demand (they pull in the convolution stack)
 
 
 def install_as_reference_modules():

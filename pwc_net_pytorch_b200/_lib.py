@@ -27,6 +27,7 @@ EXPORTS = (
     "pwc_warp_forward",
     "pwc_warp_backward",
     "pwc_warpcorr_forward",
+    "pwc_warpcorr_forward_strided",
     "pwc_warpcorr_backward_workspace",
     "pwc_warpcorr_backward",
     "pwc_last_error",
@@ -56,6 +57,9 @@ def _declare(L):
     L.pwc_warpcorr_forward.argtypes = ([_c_float_p] * 5 + [_int] * 9 + [_int, ctypes.c_float] +
                                        [_stream])
     L.pwc_warpcorr_forward.restype = _int
+    L.pwc_warpcorr_forward_strided.argtypes = ([_c_float_p] * 4 + [ctypes.c_longlong, _c_float_p] + [_int] * 9 +
+                                               [_int, ctypes.c_float] + [_stream])
+    L.pwc_warpcorr_forward_strided.restype = _int
     L.pwc_warpcorr_backward_workspace.argtypes = [_int] * 10
     L.pwc_warpcorr_backward_workspace.restype = ctypes.c_longlong
     L.pwc_warpcorr_backward.argtypes = ([_c_float_p] * 9 + [ctypes.c_void_p, ctypes.c_longlong] +

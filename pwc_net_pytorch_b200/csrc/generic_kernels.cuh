@@ -44,7 +44,7 @@ __device__ __forceinline__ float first_operand(const float* __restrict__ f1n, in
 __global__ void __launch_bounds__(256)
 corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                         const float* __restrict__ flow, float* __restrict__ out, CorrGeom g,
-                        int act, float slope)
+                        int act, float slope, long long obs)
 {
     const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +68,7 @@ corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ 
                          second_operand(f2n, flown, c, y2 + j, x2 + i, g), s);
     float v = s / (float)(g.k * g.k * g.C);
     if (act) v = leaky(v, slope);
-    out[idx] = v;
+    out[(size_t)n * (size_t)obs + (idx - (size_t)n * g.oc * g.oh * g.ow)] = v;   // obs: output batch stride
 }
 
 // correlation_cuda_kernel.cu:119-196 (gradInput1) and :211-288 (gradInput2) for stride1 == 1,

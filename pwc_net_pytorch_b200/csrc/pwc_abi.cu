@@ -67,7 +67,7 @@ bool fast_path(const pwc::CorrGeom& g)
 
 template <class Cfg, bool HAS_FLOW>
 int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
-                     float* warped, const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+                     float* warped, const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     auto kern = pwc::warpcorr_fwd_kernel<Cfg, HAS_FLOW>;
     const size_t smem = Cfg::smem_bytes(HAS_FLOW);
@@ -100,7 +100,7 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, kern, f1, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, act, slope,
-                           ksplit, cper) != cudaSuccess)
+                           ksplit, cper, obs) != cudaSuccess)
         return fail("warpcorr_fwd_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("warpcorr_fwd_kernel");
 }
@@ -153,7 +153,7 @@ bool tma_eligible(const float* f1, const float* f2, const float* out, const pwc:
 // returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
 template <int S2, int CK, bool HAS_FLOW>
 int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* out, float* warped,
-                   const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+                   const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     using Cfg = pwc::TmaCfg<S2, CK>;
     CUtensorMap m1, m2;
@@ -185,26 +185,29 @@ int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* o
     // persistent: one CTA per SM (148 on B200), each walks tiles blockIdx.x, blockIdx.x + grid, ...
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     kern<<<grid, Cfg::NT, smem, st>>>(m1, m2, m3, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles,
-                                      act, slope);
+                                      act, slope, obs);
     return check_launch("warpcorr_fwd_tma_kernel");
 }
 
 template <int S2, bool HAS_FLOW>
 int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
-                       float* warped, const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+                       float* warped, const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     if (g.W > 16)
-        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
     // small images (6x7, 12x14 levels: few CTAs, many channels): deep channel chunks, so that the
     // serial chunk loop is short and each chunk keeps many gathers in flight
     if (g.C >= 64)
-        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, (S2 == 1 ? 28 : 16)>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
-    return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, st);
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, (S2 == 1 ? 28 : 16)>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+    return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
 }
 
 int forward_impl(const float* f1, const float* f2, const float* flow, float* out, float* warped,
-                 const pwc::CorrGeom& g, int act, float slope, cudaStream_t st)
+                 const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
+    const long long dense = (long long)g.oc * g.oh * g.ow;
+    if (obs == 0) obs = dense;
+    if (obs < dense) return fail("output batch stride %lld is smaller than one image's output (%lld)", obs, dense);
     if (fast_path(g)) {
         if (warped && !flow) {   // no warp: x2_warp is x2 itself (model.py:80 with zero displacement)
             if (cudaMemcpyAsync(warped, f2, sizeof(float) * (size_t)g.B * g.C * g.H * g.W,
@@ -215,21 +218,21 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
         if (tma_eligible(f1, f2, out, g)) {
             int rc;
             if (g.s2 == 1)
-                rc = flow ? launch_fwd_tma<1, 4, true>(f1, f2, flow, out, warped, g, act, slope, st)
-                          : launch_fwd_tma<1, 4, false>(f1, f2, flow, out, warped, g, act, slope, st);
+                rc = flow ? launch_fwd_tma<1, 4, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                          : launch_fwd_tma<1, 4, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
             else
-                rc = flow ? launch_fwd_tma<2, 2, true>(f1, f2, flow, out, warped, g, act, slope, st)
-                          : launch_fwd_tma<2, 2, false>(f1, f2, flow, out, warped, g, act, slope, st);
+                rc = flow ? launch_fwd_tma<2, 2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                          : launch_fwd_tma<2, 2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
             if (rc >= 0) return rc;
         }
         if (g.s2 == 1)
-            return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, out, warped, g, act, slope, st)
-                        : dispatch_fwd_tiled<1, false>(f1, f2, flow, out, warped, g, act, slope, st);
-        return flow ? dispatch_fwd_tiled<2, true>(f1, f2, flow, out, warped, g, act, slope, st)
-                    : dispatch_fwd_tiled<2, false>(f1, f2, flow, out, warped, g, act, slope, st);
+            return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                        : dispatch_fwd_tiled<1, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+        return flow ? dispatch_fwd_tiled<2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                    : dispatch_fwd_tiled<2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
     }
     const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
-    pwc::corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f1, f2, flow, out, g, act, slope);
+    pwc::corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f1, f2, flow, out, g, act, slope, obs);
     if (!check_launch("corr_fwd_generic_kernel")) return 0;
     if (warped) {
         if (flow) return pwc_warp_forward(f2, flow, warped, g.B, g.C, g.H, g.W, st);
@@ -419,7 +422,18 @@ int pwc_warpcorr_forward(const float* f1, const float* f2, const float* flow, fl
     if (!f1 || !f2 || !out) return fail("pwc_warpcorr_forward: null pointer");
     pwc::CorrGeom g;
     if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
-    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, stream);
+    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, 0, stream);
+}
+
+int pwc_warpcorr_forward_strided(const float* f1, const float* f2, const float* flow, float* out,
+                                 long long out_batch_stride, float* warped_out, int B, int C, int H, int W,
+                                 int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                                 int act, float slope, cudaStream_t stream)
+{
+    if (!f1 || !f2 || !out) return fail("pwc_warpcorr_forward_strided: null pointer");
+    pwc::CorrGeom g;
+    if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, out_batch_stride, stream);
 }
 
 long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_flow, int, int, int,
@@ -475,7 +489,7 @@ int Correlation_forward_cuda_kernel(float* output, int ob, int oc, int oh, int o
     if (oc != g.oc || oh != g.oh || ow != g.ow)
         return fail("output is [%d,%d,%d,%d] but the parameters give [%d,%d,%d,%d]", ob, oc, oh, ow,
                     ob, g.oc, g.oh, g.ow);
-    return forward_impl(input1, input2, nullptr, output, nullptr, g, 0, 0.0f, stream);
+    return forward_impl(input1, input2, nullptr, output, nullptr, g, 0, 0.0f, 0, stream);
 }
 
 int Correlation_backward_cuda_kernel(float* gradOutput, int gob, int goc, int goh, int gow, int,

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(Cfg::NT)
 warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                     const float* __restrict__ flow, float* __restrict__ out,
                     float* __restrict__ warped_out,
-                    int C, int H, int W, int tiles_x, int tiles_y, int act, float slope, int ksplit, int cper)
+                    int C, int H, int W, int tiles_x, int tiles_y, int act, float slope, int ksplit, int cper,
+                    long long obs)
 {
     // ksplit > 1: the kernel is launched in thread-block clusters of ksplit CTAs; the CTAs of a cluster
     // share one tile and split its channels (cper each); partial accumulators are summed through
@@ -247,7 +248,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
         const bool vec = ((W & 3) == 0) && (xs + PX <= W) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            float* o = out + (((size_t)n * (D * D) + (wd * D + d)) * H + y) * W + xs;
+            float* o = out + (size_t)n * (size_t)obs + ((size_t)(wd * D + d) * H + y) * W + xs;   // obs: output batch stride
             float v[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {

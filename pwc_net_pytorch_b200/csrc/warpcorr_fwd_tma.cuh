@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
 warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2,
                         const __grid_constant__ CUtensorMap tmFlow, const float* __restrict__ f2,
                         const float* __restrict__ flow, float* __restrict__ out, float* __restrict__ warped_out,
-                        int C, int H, int W, int tiles_x, int tiles_y, int ntiles, int act, float slope)
+                        int C, int H, int W, int tiles_x, int tiles_y, int ntiles, int act, float slope,
+                        long long obs)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, HWD = Cfg::HWD;
@@ -458,7 +459,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     // 1/C (correlation_cuda_kernel.cu:65,100 divide by nelems; a correctly rounded reciprocal and one
     // multiply differ from the division by at most 1 ulp, far inside the 1e-5 tolerance)
     const float inv_nelems = __frcp_rn((float)C);
-    const bool out_32B_aligned = ((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+    const bool out_32B_aligned = ((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0) && ((obs & 7) == 0);
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
         const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
@@ -529,7 +530,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
             const bool wide = out_32B_aligned && xs + PX <= W;     // the strip is one aligned 32-byte sector
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                float* o = out + (((size_t)tc.n * (D * D) + (wd * D + d)) * H + y) * W + xs;
+                float* o = out + (size_t)tc.n * (size_t)obs + ((size_t)(wd * D + d) * H + y) * W + xs;   // obs: output batch stride
                 float v[PX];
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {

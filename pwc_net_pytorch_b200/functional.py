@@ -241,6 +241,37 @@ def warp(x, flow):
     return WarpFunction.apply(x, flow)
 
 
+def warp_correlation_into(out, x1, x2, flow, pad_size=4, kernel_size=1, max_displacement=4, stride1=1,
+                          stride2=1, act=False, slope=0.01, return_warped=False):
+    """Inference-only variant that writes the cost volume into `out`, a [B, D*D, oh, ow] *view* whose
+    images are dense but may be separated by a larger batch stride -- typically the channel slice
+    `buf[:, C:C+81]` of the flow estimator's concatenated input (model.py:89-91), so that torch.cat
+    never copies the cost volume.  No autograd graph is recorded."""
+    dev = _check_inputs(x1, x2, flow, out)
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x1, x2, flow)):
+        raise RuntimeError("warp_correlation_into is inference-only; use warp_correlation when gradients are needed")
+    if x1.shape != x2.shape or x1.dim() != 4:
+        raise ValueError("x1/x2 must be 4-D tensors of identical shape")
+    B, C, H, W = x1.shape
+    if flow is not None and tuple(flow.shape) != (B, 2, H, W):
+        raise ValueError(f"flow must be [B,2,H,W] = {(B, 2, H, W)}, got {tuple(flow.shape)}")
+    oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+    if tuple(out.shape) != (B, oc, oh, ow) or out.stride()[1:] != (oh * ow, ow, 1) or \
+            (B > 1 and out.stride(0) < oc * oh * ow):
+        raise ValueError(f"out must be a [B,{oc},{oh},{ow}] view with dense images, got shape "
+                         f"{tuple(out.shape)} strides {out.stride()}")
+    x1, x2 = x1.detach().contiguous(), x2.detach().contiguous()
+    flow = None if flow is None else flow.detach().contiguous()
+    warped = torch.empty_like(x2) if return_warped else None
+    with _on_device(dev):
+        ok = _lib.load().pwc_warpcorr_forward_strided(
+            _ptr(x1), _ptr(x2), _ptr(flow), _ptr(out), int(out.stride(0)) if B > 1 else 0, _ptr(warped),
+            B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+            int(bool(act)), float(slope), _stream())
+    _lib.check(ok, "pwc_warpcorr_forward_strided")
+    return (out, warped) if return_warped else out
+
+
 def warp_correlation(x1, x2, flow, pad_size=4, kernel_size=1, max_displacement=4, stride1=1,
                      stride2=1, act=False, slope=0.01, return_warped=False):
     return WarpCorrelationFunction.apply(x1, x2, flow, pad_size, kernel_size, max_displacement,

@@ -47,7 +47,13 @@ class FusedWarpCorrelation(nn.Module):
         return cls(pad_size=search_range * 2 + 1, kernel_size=1,
                    max_displacement=search_range * 2 + 1, stride1=1, stride2=2, **kw)
 
-    def forward(self, x1, x2, flow=None):
+    def forward(self, x1, x2, flow=None, out=None):
+        """`out` (inference only): a [B, 81, H, W] view to write into, e.g. the channel slice of the flow
+        estimator's concatenated input; see functional.warp_correlation_into."""
+        if out is not None:
+            return PF.warp_correlation_into(out, x1, x2, flow, self.pad_size, self.kernel_size,
+                                            self.max_displacement, self.stride1, self.stride2,
+                                            self.activation, self.negative_slope, self.return_warped)
         return PF.warp_correlation(x1, x2, flow, self.pad_size, self.kernel_size,
                                    self.max_displacement, self.stride1, self.stride2,
                                    self.activation, self.negative_slope, self.return_warped)

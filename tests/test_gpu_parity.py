@@ -412,6 +412,30 @@ def test_unaligned_buffers_through_the_c_abi():
     assert b"workspace" in L.pwc_last_error()
 
 
+@pytest.mark.parametrize("shape", [(3, 16, 24, 28), (2, 12, 32, 48), (2, 40, 6, 7)])
+def test_strided_output_into_concat_buffer(shape):
+    """pwc_warpcorr_forward_strided: the cost volume lands inside [x1 | corr | flow] (model.py:89-91)."""
+    B, C, H, W = shape
+    f1, f2, flow, _ = make_inputs(B, C, H, W, seed=79)
+    a, b, f = to_dev(f1, f2, flow)
+    op = pkg.FusedWarpCorrelation(*REF_CFG, activation=True, return_warped=True)
+    buf = torch.full((B, C + 81 + 2, H, W), float("nan"), device=dev())
+    buf[:, :C] = a
+    buf[:, C + 81:] = f
+    with torch.no_grad():
+        out, warped = op(a, b, f, out=buf[:, C:C + 81])
+        dense, warped2 = op(a, b, f)
+    assert out.data_ptr() == buf[:, C:C + 81].data_ptr()
+    assert torch.equal(buf, torch.cat([a, dense, f], dim=1))
+    assert torch.equal(warped, warped2)
+    a.requires_grad_()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        op(a, b, f, out=buf[:, C:C + 81])
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            op(a, b, f, out=torch.empty(B, 81, H, W + 1, device=dev())[..., :W])
+
+
 def test_cuda_graph_capture_and_stream():
     """The entry points enqueue on the caller's current stream and are graph-capturable
     (no allocation, no sync inside the library)."""
