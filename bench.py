@@ -406,24 +406,25 @@ def run_native(args):
         h2d += sum(x.numel() * 4 for x in hin)
         d2h += sum(x.numel() * 4 for x in hout)
 
-    # Double-buffered pipeline: H2D of step i+1, compute of step i and D2H of step i-1 run on three
+    # Triple-buffered pipeline: H2D of step i+1, compute of step i and D2H of step i-1 run on three
     # streams; every step's copies are inside the timed region.
     main = torch.cuda.current_stream()
     h2d_s, d2h_s = torch.cuda.Stream(), torch.cuda.Stream()
-    dev_in = [{n: [torch.empty_like(x, device=dev) for x in host[n][0]] for n in SHAPES} for _ in range(2)]
-    for b in range(2):
+    NBUF = 3
+    dev_in = [{n: [torch.empty_like(x, device=dev) for x in host[n][0]] for n in SHAPES} for _ in range(NBUF)]
+    for b in range(NBUF):
         for n in SHAPES:
             for t in dev_in[b][n][:3]:
                 t.requires_grad_()
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_done = [torch.cuda.Event() for _ in range(NBUF)]
     for e in ev_done:
         e.record(main)
 
     def e2e_step(i):
-        b = i % 2
+        b = i % NBUF
         with torch.cuda.stream(h2d_s):
-            h2d_s.wait_event(ev_done[b])          # buffer b was last used by step i - 2
+            h2d_s.wait_event(ev_done[b])          # buffer b was last used by step i - NBUF
             with torch.no_grad():
                 for n in SHAPES:
                     for dst, src in zip(dev_in[b][n], host[n][0]):
