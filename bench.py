@@ -573,6 +573,33 @@ def measure_extras(torch, pkg, dev, sets, make_set):
     pb = sum(fwd_bytes(B, C, H, W) for (C, H, W) in PYRAMID_384x448)
     out["pyramid5_fwd_B32_384x448"] = {"ms": ms, "pairs_per_s": B / (ms * 1e-3), "GBps": pb / ms / 1e6,
                                        "frac": pb / ms / 1e6 / peak}
+    # per-level table (north_star: fraction of the HBM roofline at pyramid levels 2-6), forward and
+    # backward, literal reference configuration (pad 9 / md 9 / stride2 2) and canonical md=4
+    levels = {}
+    shapes = [(f"L{6 - i}_448x384", B, C, H, W) for i, (C, H, W) in enumerate(PYRAMID_384x448)]
+    shapes += [("L2_sintel_1024x448", 16, 32, 112, 256), ("L2_kitti_1280x384", 16, 32, 96, 320),
+               ("L2_chairs_512x384_B64", 64, 32, 96, 128)]
+    for name, Bl, C, H, W in shapes:
+        a = torch.randn(Bl, C, H, W, device=dev)
+        b = torch.randn(Bl, C, H, W, device=dev)
+        f = 2.0 * torch.randn(Bl, 2, H, W, device=dev)
+        go = torch.randn(Bl, 81, H, W, device=dev)
+        row = {"B": Bl, "C": C, "H": H, "W": W}
+        for tag, o in (("canon", op), ("refcfg", op_ref)):
+            with torch.no_grad():
+                ms_f = time_cuda(torch, lambda: o(a, b, f), iters=10, warm=2)
+            a.requires_grad_(); b.requires_grad_(); f.requires_grad_()
+
+            def fb():
+                a.grad = b.grad = f.grad = None
+                o(a, b, f).backward(go)
+            ms_fb = time_cuda(torch, fb, iters=10, warm=2)
+            a.requires_grad_(False); b.requires_grad_(False); f.requires_grad_(False)
+            fbytes, bbytes = fwd_bytes(Bl, C, H, W), bwd_bytes(Bl, C, H, W)
+            row[tag] = {"fwd_ms": ms_f, "fwd_frac": fbytes / ms_f / 1e6 / peak,
+                        "bwd_ms": max(ms_fb - ms_f, 1e-6), "bwd_frac": bbytes / max(ms_fb - ms_f, 1e-6) / 1e6 / peak}
+        levels[name] = row
+    out["levels"] = levels
 
     # full PWC-Net forward (reference architecture, random init, convs on cuDNN, hot path fused):
     # the north star's "pairs/s at 448x384" figure; the conv stack is out of scope
