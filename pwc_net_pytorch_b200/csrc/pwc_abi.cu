@@ -387,7 +387,7 @@ int pwc_warp_forward(const float* x, const float* flow, float* out, int B, int C
 {
     if (!x || !flow || !out) return fail("pwc_warp_forward: null pointer");
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail("pwc_warp_forward: non-positive size");
-    constexpr int CPT = 4;
+    constexpr int CPT = 8;      // channels per thread: 8 measured best on B200 (2: 61, 4: 47, 8: 44, 16: 46 us at level 2)
     const size_t total = (size_t)B * pwc::cdiv(C, CPT) * H * W;
     pwc::warp_fwd_kernel<CPT><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, flow, out, B, C, H, W);
     return check_launch("warp_fwd_kernel");

@@ -111,8 +111,8 @@ struct TmaCfg {
     static constexpr int PXB = (NHALO + NBIL - 1) / NBIL;  // halo pixels per bilinear thread
     static constexpr int PXP = (NHALO + 31) / 32;          // halo pixels per lane of the taps warp
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 4;                           // warped-chunk ring (B -> C)
-    static constexpr int NF1 = 2 * NS;                     // f1 ring: requested NS work items ahead of use
+    static constexpr int NS = 4;                           // warped-chunk ring (B -> C); 6 measured identical
+    static constexpr int NF1 = 8;                          // f1 ring
     static constexpr int NWIN = 3;                         // f2 window ring (T -> B)
     static constexpr int WIN_ELEMS = CK * WH * WW;
     static constexpr int F1_ELEMS = CK * F1H * F1W;
