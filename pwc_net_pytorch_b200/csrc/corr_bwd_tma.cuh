@@ -42,12 +42,12 @@ struct BwdTmaCfg {
     static constexpr int WP = HWD + 4;                      // X tile pitch (TMA box width), 4 mod 8
     static constexpr int PP = TW + 4;                       // partial-slice pitch, 4 mod 8
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 4;
+    static constexpr int NS = 8;                            // X-chunk ring: deep enough to cover the TMA latency
     static constexpr int X_ELEMS = CK * HH * WP;
     static constexpr int SLICE_ELEMS = CK * TH * PP;        // one warp's partial sums for one chunk
     static constexpr int PART_ELEMS = D * SLICE_ELEMS;
     static constexpr uint32_t X_BYTES = X_ELEMS * 4;
-    static constexpr int CTRL_BYTES = 128;
+    static constexpr int CTRL_BYTES = 256;
     static constexpr int GBOX_C = 27;                       // gradient-tap prefetch box: 27 of the 81 channels
     static_assert(WP % 8 == 4 && PP % 8 == 4, "pitches must be 4 mod 8 floats");
     static_assert(X_BYTES % 128 == 0 && (PART_ELEMS * 4) % 128 == 0, "buffers stay 128B aligned");

@@ -243,8 +243,10 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
 __global__ void __launch_bounds__(256)
 warp_bwd_v4_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                    const float* __restrict__ flow, float* __restrict__ gx4,
-                   float* __restrict__ gflow, int B, int C, int H, int W, int cquads)
+                   float* __restrict__ gflow, float* __restrict__ warped_out, int B, int C, int H, int W, int cquads)
 {
+    // warped_out != nullptr: the kernel also writes the warped features (the same four corner values
+    // feed the flow gradient), which lets the fused backward skip a separate warp_fwd_kernel pass.
     const size_t HW = (size_t)H * W;
     const size_t total = (size_t)B * HW * cquads;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,7 +260,14 @@ warp_bwd_v4_kernel(const float* __restrict__ gout, const float* __restrict__ x,
     float ax = 0.0f, ay = 0.0f;
     int x0 = 0, y0 = 0;
     const Tap t = make_tap(xx, yy, u, v, H, W, &ax, &ay, &x0, &y0);
-    if (t.off < 0) return;          // nothing to scatter, zero flow gradient (the buffers are zeroed)
+    if (t.off < 0) {                // nothing to scatter, zero flow gradient (the buffers are zeroed)
+        if (warped_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (4 * cq + k < C) warped_out[((size_t)n * C + 4 * cq + k) * HW + pix] = 0.0f;
+        }
+        return;
+    }
     const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
     const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
     const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;
@@ -276,6 +285,8 @@ warp_bwd_v4_kernel(const float* __restrict__ gout, const float* __restrict__ x,
             const float v10 = m10 * __ldg(p + t.dyw), v11 = m11 * __ldg(p + t.dyw + t.dx);
             gu = fmaf(g[k], fmaf(v11 - v10, ay, (v01 - v00) * (1.0f - ay)), gu);
             gv = fmaf(g[k], fmaf(v11 - v01, ax, (v10 - v00) * (1.0f - ax)), gv);
+            if (warped_out)   // same expression as tap_sample (weights of masked corners are 0)
+                warped_out[plane + pix] = fmaf(t.w11, v11, fmaf(t.w10, v10, fmaf(t.w01, v01, t.w00 * v00)));
         }
     }
     if (gx4) {

@@ -312,30 +312,33 @@ int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float
 }
 
 // g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
+// which: 1 = g1 only, 2 = g2 only, 3 = both
 int corr_backward_impl(const float* gout, const float* gate, const float* f1, const float* second,
-                       float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st)
+                       float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st, int which = 3)
 {
     if (g.s1 != 1)
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
                     "address gradInput out of range otherwise", g.s1);
     if (fast_path(g)) {
-        if (tma_eligible(f1, second, g1, g) && (((uintptr_t)g2 | (uintptr_t)gout) & 15) == 0) {
-            int r1, r2;
+        const float* any_in = second ? second : f1;
+        float* any_out = g1 ? g1 : g2;
+        if (tma_eligible(f1, any_in, any_out, g) && (((uintptr_t)g2 | (uintptr_t)g1 | (uintptr_t)gout) & 15) == 0) {
+            int r1 = 1, r2 = 1;
             if (g.s2 == 1) {
-                r1 = launch_bwd_tma<1, 4, +1>(gout, gate, second, g1, g, slope, st);
-                r2 = r1 > 0 ? launch_bwd_tma<1, 4, -1>(gout, gate, f1, g2, g, slope, st) : r1;
+                if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(gout, gate, second, g1, g, slope, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(gout, gate, f1, g2, g, slope, st);
             } else {
-                r1 = launch_bwd_tma<2, 2, +1>(gout, gate, second, g1, g, slope, st);
-                r2 = r1 > 0 ? launch_bwd_tma<2, 2, -1>(gout, gate, f1, g2, g, slope, st) : r1;
+                if (which & 1) r1 = launch_bwd_tma<2, 2, +1>(gout, gate, second, g1, g, slope, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<2, 2, -1>(gout, gate, f1, g2, g, slope, st);
             }
             if (r1 == 0 || r2 == 0) return 0;
             if (r1 > 0 && r2 > 0) return 1;
         }
         if (g.s2 == 1)
-            return launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, st) &&
-                   launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, st);
-        return launch_bwd_tiled<2, +1>(gout, gate, second, g1, g, slope, st) &&
-               launch_bwd_tiled<2, -1>(gout, gate, f1, g2, g, slope, st);
+            return (!(which & 1) || launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, st)) &&
+                   (!(which & 2) || launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, st));
+        return (!(which & 1) || launch_bwd_tiled<2, +1>(gout, gate, second, g1, g, slope, st)) &&
+               (!(which & 2) || launch_bwd_tiled<2, -1>(gout, gate, f1, g2, g, slope, st));
     }
     const size_t total = (size_t)g.B * g.C * g.H * g.W;
     pwc::corr_bwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gout, gate, f1, second, g1, g2, g, slope);
@@ -345,7 +348,7 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
 // Feature-gradient scatter through the 4-channel-interleaved scratch (see warp_bwd_v4_kernel).
 // scratch holds B * ceil(C/4) * H * W * 4 floats, 16-byte aligned.
 int warp_backward_v4(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
-                     float* scratch, int B, int C, int H, int W, cudaStream_t stream)
+                     float* scratch, float* warped_out, int B, int C, int H, int W, cudaStream_t stream)
 {
     const int cquads = pwc::cdiv(C, 4);
     const size_t n4 = (size_t)B * cquads * H * W * 4;
@@ -355,7 +358,7 @@ int warp_backward_v4(const float* grad_out, const float* x, const float* flow, f
         return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
     const size_t total = (size_t)B * H * W * cquads;
     pwc::warp_bwd_v4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow,
-                                                                                B, C, H, W, cquads);
+                                                                                warped_out, B, C, H, W, cquads);
     if (!check_launch("warp_bwd_v4_kernel")) return 0;
     pwc::deinterleave4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cquads);
     return check_launch("deinterleave4_kernel");
@@ -464,15 +467,26 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     const size_t N = (size_t)B * C * H * W;
     float* wbuf = static_cast<float*>(workspace);
     float* gwarped = wbuf + N;
+    float* scratch = gwarped + N;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
+    const bool split_ok = fast_path(g);      // the tiled kernels compute the two gradients in separate launches
+    if (vec_ok && split_ok) {
+        // 1. gradient w.r.t. the warped features (needs f1 and grad_out only)
+        if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2)) return 0;
+        // 2. scatter to grad_f2 + flow gradient; the same pass re-materialises x2_warp when the forward did
+        //    not export it (both need the four bilinear corner values)
+        if (!warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, warped_in ? nullptr : wbuf, B, C, H, W, stream))
+            return 0;
+        // 3. gradient w.r.t. f1 (needs x2_warp)
+        return corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1);
+    }
     const float* warped = warped_in;
     if (!warped) {      // re-materialise x2_warp (the forward never stored it)
         if (!pwc_warp_forward(f2, flow, wbuf, B, C, H, W, stream)) return 0;
         warped = wbuf;
     }
     if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream)) return 0;
-    float* scratch = gwarped + N;
-    if ((reinterpret_cast<uintptr_t>(scratch) & 15) == 0)
-        return warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, B, C, H, W, stream);
+    if (vec_ok) return warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, nullptr, B, C, H, W, stream);
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
 }
 
