@@ -70,16 +70,21 @@ corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
     const float nelems = (float)C;
     const int c_begin = blockIdx.y * cgroup;
     const int c_end = min(C, c_begin + cgroup);
+    // The halo tile is zero outside the image: zero the buffer once, then every chunk only rewrites the
+    // rectangle that intersects the image (for the 6x7 / 12x14 levels that is a small part of the tile).
+    for (int i = tid; i < CK * HH * HP; i += NT) sX[i] = 0.0f;
+    const int ry0 = max(0, y0t - R), ry1 = min(H, y0t + TH + R);
+    const int rx0 = max(0, x0t - R), rx1 = min(W, x0t + TW + R);
+    const int rw = rx1 - rx0, rh = ry1 - ry0, rarea = rw * rh;
     for (int c0 = c_begin; c0 < c_end; c0 += CK) {
         __syncthreads();
-        for (int i = tid; i < CK * HH * HWD; i += NT) {
-            const int c = i / (HH * HWD), rem = i - c * (HH * HWD);
-            const int hy = rem / HWD, hx = rem - hy * HWD;
-            const int yy = y0t - R + hy, xx = x0t - R + hx;
-            float v = 0.0f;
-            if (c0 + c < c_end && yy >= 0 && yy < H && xx >= 0 && xx < W)
-                v = __ldg(Xn + (size_t)(c0 + c) * HW + (size_t)yy * W + xx);
-            sX[c * (HH * HP) + hy * HP + hx] = v;
+        const int nch = min(CK, c_end - c0);
+        for (int i = tid; i < nch * rarea; i += NT) {
+            const int c = i / rarea, rem = i - c * rarea;
+            const int ry = rem / rw, rx = rem - ry * rw;
+            const int yy = ry0 + ry, xx = rx0 + rx;
+            sX[c * (HH * HP) + (yy - (y0t - R)) * HP + (xx - (x0t - R))] =
+                __ldg(Xn + (size_t)(c0 + c) * HW + (size_t)yy * W + xx);
         }
         __syncthreads();
         const float* base = sX + (ly + R) * HP + (lx + R);
