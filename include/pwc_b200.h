@@ -45,7 +45,7 @@ extern "C" {
 typedef struct CUstream_st *cudaStream_t;
 #endif
 
-#define PWC_B200_ABI_VERSION 2
+#define PWC_B200_ABI_VERSION 3
 
 /* ---- legacy launchers: correlation_cuda_kernel.h:5-39 ------------------------------------- */
 int Correlation_forward_cuda_kernel(
@@ -135,6 +135,9 @@ int pwc_set_force_generic(int on);
 /* disables the TMA-staged forward kernel (falls back to the plain tiled kernel); test hook,
  * returns the previous value. */
 int pwc_set_disable_tma(int on);
+/* disables the whole-image kernels of the coarse pyramid levels (H*W <= 256), so that the tiled
+ * kernels serve those shapes too; test hook, returns the previous value. */
+int pwc_set_disable_small(int on);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ EXPORTS = (
     "pwc_launch_count",
     "pwc_set_force_generic",
     "pwc_set_disable_tma",
+    "pwc_set_disable_small",
 )
 
 
@@ -75,6 +76,8 @@ def _declare(L):
     L.pwc_set_force_generic.restype = _int
     L.pwc_set_disable_tma.argtypes = [_int]
     L.pwc_set_disable_tma.restype = _int
+    L.pwc_set_disable_small.argtypes = [_int]
+    L.pwc_set_disable_small.restype = _int
 
 
 def load():
@@ -90,7 +93,7 @@ def load():
                     "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
             L = ctypes.CDLL(LIB_PATH)
             _declare(L)
-            if L.pwc_abi_version() != 2:
+            if L.pwc_abi_version() != 3:
                 raise RuntimeError("libpwc_b200.so ABI version mismatch; rebuild it")
             _lib = L
     return _lib

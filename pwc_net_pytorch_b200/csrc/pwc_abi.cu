@@ -11,6 +11,7 @@
 #include "corr_bwd_tma.cuh"
 #include "generic_kernels.cuh"
 #include "pwc_common.cuh"
+#include "small_image.cuh"
 #include "warpcorr_fwd.cuh"
 #include "warpcorr_fwd_tma.cuh"
 
@@ -20,6 +21,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_disable_tma{0};
+std::atomic<int> g_disable_small{0};
 
 int fail(const char* fmt, ...)
 {
@@ -103,6 +105,71 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
                            ksplit, cper, obs) != cudaSuccess)
         return fail("warpcorr_fwd_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("warpcorr_fwd_kernel");
+}
+
+
+// ---- whole-image path for the coarse levels (small_image.cuh) -----------------------------------
+constexpr size_t SMALL_SMEM_LIMIT = 200 * 1024;
+
+bool small_eligible(const pwc::CorrGeom& g, bool has_flow, bool backward)
+{
+    if (g_disable_small.load() || !fast_path(g) || (long long)g.H * g.W > pwc::SMALL_MAX_PX) return false;
+    const pwc::SmallPlan p = pwc::small_plan(g.C);
+    const size_t smem = backward ? pwc::small_bwd_smem(g.H * g.W, p, has_flow) : pwc::small_fwd_smem(g.H * g.W, p, has_flow);
+    return smem <= SMALL_SMEM_LIMIT && (long long)g.B * p.ks <= 0x3fffffffLL;
+}
+
+template <class Kern, class... Args>
+int launch_small(Kern kern, const char* what, size_t smem, int B, int ks, cudaStream_t st, Args... args)
+{
+    // the shared-memory opt-in is per (function, device): remember which instantiations have it
+    static thread_local const void* configured[16];
+    static thread_local int configured_dev = -1, nconfigured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) { nconfigured = 0; configured_dev = dev; }
+    bool seen = false;
+    for (int i = 0; i < nconfigured; ++i) seen |= configured[i] == reinterpret_cast<const void*>(kern);
+    if (!seen) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_LIMIT) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", SMALL_SMEM_LIMIT, cudaGetErrorString(cudaGetLastError()));
+        if (nconfigured < 16) configured[nconfigured++] = reinterpret_cast<const void*>(kern);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * ks));
+    cfg.blockDim = dim3(pwc::SMALL_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, args...) != cudaSuccess)
+        return fail("%s launch: %s", what, cudaGetErrorString(cudaGetLastError()));
+    return check_launch(what);
+}
+
+template <int S2, bool HAS_FLOW>
+int launch_fwd_small(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+                     const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
+{
+    const pwc::SmallPlan p = pwc::small_plan(g.C);
+    return launch_small(pwc::warpcorr_fwd_small_kernel<S2, HAS_FLOW>, "warpcorr_fwd_small_kernel",
+                        pwc::small_fwd_smem(g.H * g.W, p, HAS_FLOW), g.B, p.ks, st, f1, f2, flow, out, warped, g.C, g.H,
+                        g.W, p.cs, p.csp, act, slope, obs);
+}
+
+template <int S2, bool HAS_FLOW>
+int launch_bwd_small(const float* gout, const float* gate, const float* f1, const float* f2, const float* flow,
+                     float* gf1, float* gf2, float* gflow, const pwc::CorrGeom& g, float slope, cudaStream_t st)
+{
+    const pwc::SmallPlan p = pwc::small_plan(g.C);
+    return launch_small(pwc::warpcorr_bwd_small_kernel<S2, HAS_FLOW>, "warpcorr_bwd_small_kernel",
+                        pwc::small_bwd_smem(g.H * g.W, p, HAS_FLOW), g.B, p.ks, st, gout, gate, f1, f2, flow, gf1, gf2,
+                        gflow, g.C, g.H, g.W, p.cs, p.csp, slope);
 }
 
 
@@ -215,6 +282,13 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
                 return fail("cudaMemcpyAsync(warped_out): %s", cudaGetErrorString(cudaGetLastError()));
             warped = nullptr;
         }
+        if (small_eligible(g, flow != nullptr, false)) {
+            if (g.s2 == 1)
+                return flow ? launch_fwd_small<1, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                            : launch_fwd_small<1, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+            return flow ? launch_fwd_small<2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
+                        : launch_fwd_small<2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+        }
         if (tma_eligible(f1, f2, out, g)) {
             int rc;
             if (g.s2 == 1)
@@ -319,6 +393,9 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
     if (g.s1 != 1)
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
                     "address gradInput out of range otherwise", g.s1);
+    if (which == 3 && small_eligible(g, false, true))
+        return g.s2 == 1 ? launch_bwd_small<1, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st)
+                         : launch_bwd_small<2, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st);
     if (fast_path(g)) {
         const float* any_in = second ? second : f1;
         float* any_out = g1 ? g1 : g2;
@@ -373,6 +450,7 @@ int pwc_abi_version(void) { return PWC_B200_ABI_VERSION; }
 long long pwc_launch_count(void) { return g_launches.load(); }
 int pwc_set_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 int pwc_set_disable_tma(int on) { return g_disable_tma.exchange(on ? 1 : 0); }
+int pwc_set_disable_small(int on) { return g_disable_small.exchange(on ? 1 : 0); }
 
 int pwc_corr_output_shape(int H, int W, int pad_size, int kernel_size, int max_displacement,
                           int stride1, int stride2, int* out_channels, int* out_h, int* out_w)
@@ -460,6 +538,9 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     const float* gate = act ? out : nullptr;
     if (!flow) return corr_backward_impl(grad_out, gate, f1, f2, grad_f1, grad_f2, g, slope, stream);
     if (!grad_flow) return fail("pwc_warpcorr_backward: grad_flow is required when flow is given");
+    if (small_eligible(g, true, true))      // coarse levels: the whole backward is one launch, no workspace
+        return g.s2 == 1 ? launch_bwd_small<1, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream)
+                         : launch_bwd_small<2, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream);
     const long long need = pwc_warpcorr_backward_workspace(B, C, H, W, 1, pad_size, kernel_size,
                                                            max_displacement, stride1, stride2);
     if (!workspace || workspace_bytes < need)

@@ -489,3 +489,65 @@ def test_cuda_graph_capture_and_stream():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(captured, eager)
+
+
+SMALL_SHAPES = [(2, 196, 6, 7), (2, 192, 6, 8), (2, 128, 12, 14), (1, 128, 12, 16), (1, 5, 9, 11), (1, 17, 2, 2),
+                (2, 64, 16, 16), (1, 3, 1, 1), (1, 260, 6, 8), (1, 33, 7, 16)]
+
+
+@pytest.mark.parametrize("shape", SMALL_SHAPES)
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+@pytest.mark.parametrize("act", [False, True])
+def test_small_image_kernels_vs_oracle_and_tiled(shape, cfg, act):
+    """Coarse pyramid levels (H*W <= 256) run on the whole-image cluster kernels (one launch forward,
+    one launch backward); they must agree with the oracle and with the tiled kernels that serve the
+    same shapes when the small path is switched off."""
+    B, C, H, W = shape
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=C + 7 * H + W)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    L = _lib.load()
+    res = []
+    for disable in (0, 1):
+        prev = L.pwc_set_disable_small(disable)
+        try:
+            a, b, f, g = to_dev(f1, f2, flow, go)
+            for t in (a, b, f):
+                t.requires_grad_()
+            before = L.pwc_launch_count()
+            out, warped = pkg.FusedWarpCorrelation(*cfg, activation=act, return_warped=True)(a, b, f)
+            out.backward(g)
+            torch.cuda.synchronize()
+            launches = L.pwc_launch_count() - before
+            res.append([out.detach(), warped.detach(), a.grad.clone(), b.grad.clone(), f.grad.clone()])
+        finally:
+            L.pwc_set_disable_small(prev)
+        if not disable:
+            assert launches == 2, launches          # one forward + one backward launch, nothing else
+    ref, ref_w = co.warpcorr_forward(f1, f2, flow, *cfg, act=act, slope=0.01, return_warped=True)
+    gate = res[0][0].cpu().numpy()      # sign gate of the GPU's own forward (values near 0 may flip sign)
+    g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, gate, *cfg, act=act, slope=0.01)
+    for got, want in zip(res[0], (ref, ref_w, g1, g2, gf)):
+        assert max_rel(got.cpu().numpy(), want) < TOL
+    for x, y in zip(*res):
+        assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 5e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 196, 6, 7), (1, 40, 12, 14), (1, 3, 5, 5)])
+@pytest.mark.parametrize("cfg", [REF_CFG, CANON_CFG])
+def test_small_image_plain_correlation(shape, cfg):
+    """Legacy Correlation (no warp) at the coarse levels: forward and both gradients in one launch each."""
+    B, C, H, W = shape
+    f1, f2, _, rng = make_inputs(B, C, H, W, seed=91)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    a, b, g = to_dev(f1, f2, go)
+    a.requires_grad_(); b.requires_grad_()
+    L = _lib.load()
+    before = L.pwc_launch_count()
+    out = pkg.Correlation(*cfg)(a, b)
+    out.backward(g)
+    torch.cuda.synchronize()
+    assert L.pwc_launch_count() - before == 2
+    assert max_rel(out.detach().cpu().numpy(), co.corr_forward(f1, f2, *cfg)) < TOL
+    g1, g2 = co.corr_backward(go, f1, f2, *cfg)
+    assert max_rel(a.grad.cpu().numpy(), g1) < TOL
+    assert max_rel(b.grad.cpu().numpy(), g2) < TOL
