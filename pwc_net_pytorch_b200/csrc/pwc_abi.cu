@@ -111,12 +111,27 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
 // ---- whole-image path for the coarse levels (small_image.cuh) -----------------------------------
 constexpr size_t SMALL_SMEM_LIMIT = 200 * 1024;
 
-bool small_eligible(const pwc::CorrGeom& g, bool has_flow, bool backward)
+int sm_count_of_current_device()
 {
-    if (g_disable_small.load() || !fast_path(g) || (long long)g.H * g.W > pwc::SMALL_MAX_PX) return false;
-    const pwc::SmallPlan p = pwc::small_plan(g.C);
-    const size_t smem = backward ? pwc::small_bwd_smem(g.H * g.W, p, has_flow) : pwc::small_fwd_smem(g.H * g.W, p, has_flow);
-    return smem <= SMALL_SMEM_LIMIT && (long long)g.B * p.ks <= 0x3fffffffLL;
+    static thread_local int dev_cached = -1, count = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) {
+        if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) count = 148;
+        (void)cudaGetLastError();
+        dev_cached = dev;
+    }
+    return count;
+}
+
+pwc::SmallPlan small_plan_for(const pwc::CorrGeom& g, bool has_flow, bool backward)
+{
+    pwc::SmallPlan none = {0, 0, 0, 0, false};
+    if (g_disable_small.load() || !fast_path(g) || (long long)g.H * g.W > pwc::SMALL_MAX_PX) return none;
+    const pwc::SmallPlan p = pwc::small_plan(g.B, g.C, g.H * g.W, has_flow, backward, SMALL_SMEM_LIMIT,
+                                             sm_count_of_current_device());
+    if (!p.ok || (long long)g.B * p.ks > 0x3fffffffLL) return none;
+    return p;
 }
 
 template <class Kern, class... Args>
@@ -156,9 +171,8 @@ template <int S2, bool HAS_FLOW>
 int launch_fwd_small(const float* f1, const float* f2, const float* flow, float* out, float* warped,
                      const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
-    const pwc::SmallPlan p = pwc::small_plan(g.C);
-    return launch_small(pwc::warpcorr_fwd_small_kernel<S2, HAS_FLOW>, "warpcorr_fwd_small_kernel",
-                        pwc::small_fwd_smem(g.H * g.W, p, HAS_FLOW), g.B, p.ks, st, f1, f2, flow, out, warped, g.C, g.H,
+    const pwc::SmallPlan p = small_plan_for(g, HAS_FLOW, false);
+    return launch_small(pwc::warpcorr_fwd_small_kernel<S2, HAS_FLOW>, "warpcorr_fwd_small_kernel", p.smem, g.B, p.ks, st, f1, f2, flow, out, warped, g.C, g.H,
                         g.W, p.cs, p.csp, act, slope, obs);
 }
 
@@ -166,9 +180,8 @@ template <int S2, bool HAS_FLOW>
 int launch_bwd_small(const float* gout, const float* gate, const float* f1, const float* f2, const float* flow,
                      float* gf1, float* gf2, float* gflow, const pwc::CorrGeom& g, float slope, cudaStream_t st)
 {
-    const pwc::SmallPlan p = pwc::small_plan(g.C);
-    return launch_small(pwc::warpcorr_bwd_small_kernel<S2, HAS_FLOW>, "warpcorr_bwd_small_kernel",
-                        pwc::small_bwd_smem(g.H * g.W, p, HAS_FLOW), g.B, p.ks, st, gout, gate, f1, f2, flow, gf1, gf2,
+    const pwc::SmallPlan p = small_plan_for(g, HAS_FLOW, true);
+    return launch_small(pwc::warpcorr_bwd_small_kernel<S2, HAS_FLOW>, "warpcorr_bwd_small_kernel", p.smem, g.B, p.ks, st, gout, gate, f1, f2, flow, gf1, gf2,
                         gflow, g.C, g.H, g.W, p.cs, p.csp, slope);
 }
 
@@ -282,7 +295,7 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
                 return fail("cudaMemcpyAsync(warped_out): %s", cudaGetErrorString(cudaGetLastError()));
             warped = nullptr;
         }
-        if (small_eligible(g, flow != nullptr, false)) {
+        if (small_plan_for(g, flow != nullptr, false).ok) {
             if (g.s2 == 1)
                 return flow ? launch_fwd_small<1, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
                             : launch_fwd_small<1, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
@@ -393,7 +406,7 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
     if (g.s1 != 1)
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
                     "address gradInput out of range otherwise", g.s1);
-    if (which == 3 && small_eligible(g, false, true))
+    if (which == 3 && small_plan_for(g, false, true).ok)
         return g.s2 == 1 ? launch_bwd_small<1, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st)
                          : launch_bwd_small<2, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st);
     if (fast_path(g)) {
@@ -538,7 +551,7 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     const float* gate = act ? out : nullptr;
     if (!flow) return corr_backward_impl(grad_out, gate, f1, f2, grad_f1, grad_f2, g, slope, stream);
     if (!grad_flow) return fail("pwc_warpcorr_backward: grad_flow is required when flow is given");
-    if (small_eligible(g, true, true))      // coarse levels: the whole backward is one launch, no workspace
+    if (small_plan_for(g, true, true).ok)      // coarse levels: the whole backward is one launch, no workspace
         return g.s2 == 1 ? launch_bwd_small<1, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream)
                          : launch_bwd_small<2, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream);
     const long long need = pwc_warpcorr_backward_workspace(B, C, H, W, 1, pad_size, kernel_size,

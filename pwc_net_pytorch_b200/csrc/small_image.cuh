@@ -20,31 +20,47 @@
 namespace pwc {
 
 constexpr int SMALL_MAX_PX = 256;
-constexpr int SMALL_NT = 512;
+constexpr int SMALL_NT = 768;
 constexpr int SMALL_MAX_KS = 8;      // portable cluster size
 
-// Channel slice per CTA: a multiple of 4, at most SMALL_MAX_KS slices; ks is a power of two.
+// Channel slice per CTA (cs, a multiple of 4; pitch csp with csp/4 odd) and cluster size ks (a power
+// of two).  The largest ks whose B*ks CTAs still run as ONE wave (one CTA per SM) wins: these levels
+// are latency-bound, a second wave costs a whole kernel time.
 struct SmallPlan {
     int cs, csp, ks;
+    size_t smem;
+    bool ok;
 };
-inline SmallPlan small_plan(int C)
+inline size_t small_smem(int HW, int csp, bool has_flow, bool backward)
 {
-    SmallPlan p;
-    p.cs = 4 * cdiv(C, 4 * SMALL_MAX_KS);
-    p.csp = ((p.cs / 4) & 1) ? p.cs : p.cs + 4;
-    const int need = cdiv(C, p.cs);
-    p.ks = 1;
-    while (p.ks < need) p.ks *= 2;
-    return p;
+    const size_t common = (size_t)round_up(81 * HW, 4);
+    if (!backward) return sizeof(float) * ((size_t)2 * HW * csp + common + (has_flow ? (size_t)6 * HW : 0));
+    return sizeof(float) * ((size_t)(has_flow ? 3 : 2) * HW * csp + common + (has_flow ? (size_t)12 * HW : 0));
 }
-inline size_t small_fwd_smem(int HW, const SmallPlan& p, bool has_flow)
+inline SmallPlan small_plan(int B, int C, int HW, bool has_flow, bool backward, size_t smem_limit, int sm_count)
 {
-    return sizeof(float) * ((size_t)2 * HW * p.csp + (size_t)round_up(81 * HW, 4) + (has_flow ? (size_t)6 * HW : 0));
+    SmallPlan best = {0, 0, 0, 0, false};
+    for (int ks = SMALL_MAX_KS; ks >= 1; ks >>= 1) {
+        SmallPlan p;
+        p.cs = 4 * cdiv(C, 4 * ks);
+        p.csp = ((p.cs / 4) & 1) ? p.cs : p.cs + 4;
+        p.ks = 1;
+        while (p.ks < cdiv(C, p.cs)) p.ks *= 2;      // few channels: fewer slices than asked for
+        p.smem = small_smem(HW, p.csp, has_flow, backward);
+        p.ok = p.smem <= smem_limit;
+        if (!p.ok) break;                            // fewer slices only need more shared memory
+        best = p;
+        if ((long long)B * p.ks <= sm_count) break;
+    }
+    return best;
 }
-inline size_t small_bwd_smem(int HW, const SmallPlan& p, bool has_flow)
+
+// valid displacement steps t in [-4, 4] with 0 <= v + t*S2 < n
+template <int S2>
+__device__ __forceinline__ void disp_range(int v, int n, int& lo, int& hi)
 {
-    return sizeof(float) * ((size_t)(has_flow ? 3 : 2) * HW * p.csp + (size_t)round_up(81 * HW, 4) +
-                            (has_flow ? (size_t)12 * HW : 0));
+    lo = max(-4, -(v / S2));
+    hi = min(4, (n - 1 - v) / S2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,9 +81,9 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
     const int n = blockIdx.x / ks;
     const int tid = threadIdx.x;
     const int HW = H * W;
-    const int nq = cs >> 2;
     const int c_begin = rank * cs;
     const int nch = max(0, min(cs, C - c_begin));       // a trailing rank may own no channel at all
+    const int nq = (nch + 3) >> 2;                      // channel quads in use
 
     extern __shared__ __align__(16) float smem[];
     float* sF1 = smem;                                   // [HW][csp]
@@ -88,11 +104,15 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
             sTapO[q] = make_int2(tp.off, (tp.dyw << 1) | tp.dx);
         }
     }
+    // loads are unconditional (channel index clamped into the slice) so that all of a thread's
+    // requests are in flight together; the tail channels of the last quad are zeroed afterwards
     for (int i = tid; i < HW * nq; i += NT) {
         const int q4 = i / HW, p = i - q4 * HW;
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (4 * q4 + k < nch) ? __ldg(f1n + (size_t)(4 * q4 + k) * HW + p) : 0.0f;
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(f1n + (size_t)min(4 * q4 + k, nch - 1) * HW + p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (4 * q4 + k < nch) ? v[k] : 0.0f;
         *reinterpret_cast<float4*>(sF1 + p * csp + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
     }
     if (HAS_FLOW) __syncthreads();
@@ -106,20 +126,22 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
             const int2 o = sTapO[q];
             if (o.x >= 0) {
                 const int dx = o.y & 1, dyw = o.y >> 1;
+                float c00[4], c01[4], c10[4], c11[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (4 * q4 + k < nch) {
-                        const float* p = f2n + (size_t)(4 * q4 + k) * HW + o.x;
-                        const float v00 = __ldg(p), v01 = __ldg(p + dx);
-                        const float v10 = __ldg(p + dyw), v11 = __ldg(p + dyw + dx);
-                        v[k] = fmaf(w.w, v11, fmaf(w.z, v10, fmaf(w.y, v01, w.x * v00)));
-                    }
+                    const float* p = f2n + (size_t)min(4 * q4 + k, nch - 1) * HW + o.x;
+                    c00[k] = __ldg(p); c01[k] = __ldg(p + dx);
+                    c10[k] = __ldg(p + dyw); c11[k] = __ldg(p + dyw + dx);
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    v[k] = (4 * q4 + k < nch) ? fmaf(w.w, c11[k], fmaf(w.z, c10[k], fmaf(w.y, c01[k], w.x * c00[k]))) : 0.0f;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (4 * q4 + k < nch) v[k] = __ldg(f2n + (size_t)(4 * q4 + k) * HW + q);
+            for (int k = 0; k < 4; ++k) v[k] = __ldg(f2n + (size_t)min(4 * q4 + k, nch - 1) * HW + q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (4 * q4 + k < nch) ? v[k] : 0.0f;
         }
         *reinterpret_cast<float4*>(sW2 + q * csp + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
         if (HAS_FLOW && warped_out != nullptr) {     // x2_warp export (model.py:107,113)
@@ -174,10 +196,12 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
         const float nelems = (float)C;   // correlation_cuda_kernel.cu:65,100
         float* on = out + (size_t)n * (size_t)obs;
         for (int o = lo + tid; o < hi; o += NT) {
+            float part[SMALL_MAX_KS];
+#pragma unroll
+            for (int rr = 0; rr < SMALL_MAX_KS; ++rr) part[rr] = (rr < ks) ? remote[rr][o] : 0.0f;
             float s = 0.0f;
 #pragma unroll
-            for (int rr = 0; rr < SMALL_MAX_KS; ++rr)
-                if (rr < ks) s += remote[rr][o];
+            for (int rr = 0; rr < SMALL_MAX_KS; ++rr) s += part[rr];
             s = s / nelems;
             if (act) s = leaky(s, slope);
             on[o] = s;
@@ -193,6 +217,7 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
 //   g1[c,p]  = 1/C * sum_d gO'[d, p]   * W2[c, p+d]                      (correlation_cuda_kernel.cu:108-198)
 //   gf2      = bilinear scatter of gW2, gflow = sum_c gW2 * dW2/d(u,v)   (grid_sample backward)
 // Without flow W2 = f2 and gf2 = gW2 (the legacy Correlation backward).
+// Only displacements that stay inside the image are visited (a quarter of the 81 at the 6x7 level).
 // ---------------------------------------------------------------------------------------------
 template <int S2, bool HAS_FLOW>
 __global__ void __launch_bounds__(SMALL_NT)
@@ -209,9 +234,9 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
     const int n = blockIdx.x / ks;
     const int tid = threadIdx.x;
     const int HW = H * W;
-    const int nq = cs >> 2;
     const int c_begin = rank * cs;
     const int nch = max(0, min(cs, C - c_begin));
+    const int nq = (nch + 3) >> 2;
 
     extern __shared__ __align__(16) float smem[];
     float* sF1 = smem;                                   // [HW][csp]
@@ -241,7 +266,9 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
         const int q4 = i / HW, p = i - q4 * HW;
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (4 * q4 + k < nch) ? __ldg(f1n + (size_t)(4 * q4 + k) * HW + p) : 0.0f;
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(f1n + (size_t)min(4 * q4 + k, nch - 1) * HW + p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (4 * q4 + k < nch) ? v[k] : 0.0f;
         *reinterpret_cast<float4*>(sF1 + p * csp + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
     }
     if (HAS_FLOW) {
@@ -271,42 +298,53 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
         const int q4 = i / HW, q = i - q4 * HW;
         const int y = q / W, x = q - y * W;
 
-        // gradient w.r.t. the warped features at q
+        // issue the global gathers first: they land while gW2 is computed out of shared memory
+        float c00[4], c01[4], c10[4], c11[4];
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 o = make_int4(-1, 0, 0, 0);
+        float2 a = make_float2(0.f, 0.f);
+        if (HAS_FLOW) {
+            w = sTapW[q];
+            o = sTapO[q];
+            a = sTapA[q];
+            const int off = max(o.x, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float* p = f2n + (size_t)min(4 * q4 + k, nch - 1) * HW + off;
+                c00[k] = __ldg(p); c01[k] = __ldg(p + o.y);
+                c10[k] = __ldg(p + o.z); c11[k] = __ldg(p + o.z + o.y);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c00[k] = __ldg(f2n + (size_t)min(4 * q4 + k, nch - 1) * HW + q);
+        }
+
+        // gradient w.r.t. the warped features at q: source pixels p = q - d inside the image
         float gw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int tji = 0; tji < D; ++tji) {
-            const int py = y - (tji - r) * S2;
-            if (py >= 0 && py < H) {
-#pragma unroll
-                for (int ti = 0; ti < D; ++ti) {
-                    const int px = x - (ti - r) * S2;
-                    if (px >= 0 && px < W) {
-                        const int p = py * W + px;
-                        const float g = sG[(tji * D + ti) * HW + p];
-                        const float4 f = *reinterpret_cast<const float4*>(sF1 + p * csp + 4 * q4);
-                        gw[0] = fmaf(g, f.x, gw[0]); gw[1] = fmaf(g, f.y, gw[1]);
-                        gw[2] = fmaf(g, f.z, gw[2]); gw[3] = fmaf(g, f.w, gw[3]);
-                    }
+        {
+            int tlo, thi, slo, shi;
+            disp_range<S2>(H - 1 - y, H, tlo, thi);      // 0 <= y - t*S2 < H  <=>  range of (H-1-y) + t*S2
+            disp_range<S2>(W - 1 - x, W, slo, shi);
+            for (int t = tlo; t <= thi; ++t) {
+                const int prow = (y - t * S2) * W + x;
+                const float* gr = sG + ((t + r) * D + r) * HW + prow;
+                for (int s = slo; s <= shi; ++s) {
+                    const float g = gr[s * (HW - S2)];                       // sG[d][prow - s*S2]
+                    const float4 f = *reinterpret_cast<const float4*>(sF1 + (prow - s * S2) * csp + 4 * q4);
+                    gw[0] = fmaf(g, f.x, gw[0]); gw[1] = fmaf(g, f.y, gw[1]);
+                    gw[2] = fmaf(g, f.z, gw[2]); gw[3] = fmaf(g, f.w, gw[3]);
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gw[k] = gw[k] / nelems;
+        for (int k = 0; k < 4; ++k) gw[k] = (4 * q4 + k < nch) ? gw[k] / nelems : 0.0f;
 
         if (!HAS_FLOW) {
-            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (4 * q4 + k < nch) {
-                    v[k] = __ldg(f2n + (size_t)(4 * q4 + k) * HW + q);
-                    gf2[((size_t)n * C + c_begin + 4 * q4 + k) * HW + q] = gw[k];
-                }
-            }
-            *reinterpret_cast<float4*>(sW2 + q * csp + 4 * q4) = make_float4(v[0], v[1], v[2], v[3]);
+            for (int k = 0; k < 4; ++k)
+                if (4 * q4 + k < nch) gf2[((size_t)n * C + c_begin + 4 * q4 + k) * HW + q] = gw[k];
+            *reinterpret_cast<float4*>(sW2 + q * csp + 4 * q4) = make_float4(c00[0], c00[1], c00[2], c00[3]);
         } else {
-            const float4 w = sTapW[q];
-            const int4 o = sTapO[q];
-            const float2 a = sTapA[q];
             float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (o.x >= 0) {
                 const float m00 = (o.w & 1) ? 1.0f : 0.0f, m01 = (o.w & 2) ? 1.0f : 0.0f;
@@ -314,14 +352,10 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
                 float gu = 0.0f, gv = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (4 * q4 + k < nch) {
-                        const float* p = f2n + (size_t)(4 * q4 + k) * HW + o.x;
-                        const float v00 = m00 * __ldg(p), v01 = m01 * __ldg(p + o.y);
-                        const float v10 = m10 * __ldg(p + o.z), v11 = m11 * __ldg(p + o.z + o.y);
-                        v[k] = fmaf(w.w, v11, fmaf(w.z, v10, fmaf(w.y, v01, w.x * v00)));
-                        gu = fmaf(gw[k], fmaf(v11 - v10, a.y, (v01 - v00) * (1.0f - a.y)), gu);
-                        gv = fmaf(gw[k], fmaf(v11 - v01, a.x, (v10 - v00) * (1.0f - a.x)), gv);
-                    }
+                    const float v00 = m00 * c00[k], v01 = m01 * c01[k], v10 = m10 * c10[k], v11 = m11 * c11[k];
+                    v[k] = fmaf(w.w, v11, fmaf(w.z, v10, fmaf(w.y, v01, w.x * v00)));
+                    gu = fmaf(gw[k], fmaf(v11 - v10, a.y, (v01 - v00) * (1.0f - a.y)), gu);
+                    gv = fmaf(gw[k], fmaf(v11 - v01, a.x, (v10 - v00) * (1.0f - a.x)), gv);
                 }
                 float* t = sGF2 + o.x * csp + 4 * q4;
                 const int sdx = o.y * csp, sdy = o.z * csp;   // o.y is 0 or 1 pixel, o.z is 0 or W pixels
@@ -345,24 +379,21 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
         const int q4 = i / HW, p = i - q4 * HW;
         const int y = p / W, x = p - y * W;
         float g1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int tji = 0; tji < D; ++tji) {
-            const int y2 = y + (tji - r) * S2;
-            if (y2 >= 0 && y2 < H) {
-#pragma unroll
-                for (int ti = 0; ti < D; ++ti) {
-                    const int x2 = x + (ti - r) * S2;
-                    if (x2 >= 0 && x2 < W) {
-                        const float g = sG[(tji * D + ti) * HW + p];
-                        const float4 wv = *reinterpret_cast<const float4*>(sW2 + (y2 * W + x2) * csp + 4 * q4);
-                        g1[0] = fmaf(g, wv.x, g1[0]); g1[1] = fmaf(g, wv.y, g1[1]);
-                        g1[2] = fmaf(g, wv.z, g1[2]); g1[3] = fmaf(g, wv.w, g1[3]);
-                    }
-                }
+        int tlo, thi, slo, shi;
+        disp_range<S2>(y, H, tlo, thi);
+        disp_range<S2>(x, W, slo, shi);
+        for (int t = tlo; t <= thi; ++t) {
+            const float* gr = sG + ((t + r) * D + r) * HW + p;
+            const float* wr = sW2 + ((y + t * S2) * W + x) * csp + 4 * q4;
+            for (int s = slo; s <= shi; ++s) {
+                const float g = gr[s * HW];
+                const float4 wv = *reinterpret_cast<const float4*>(wr + s * S2 * csp);
+                g1[0] = fmaf(g, wv.x, g1[0]); g1[1] = fmaf(g, wv.y, g1[1]);
+                g1[2] = fmaf(g, wv.z, g1[2]); g1[3] = fmaf(g, wv.w, g1[3]);
             }
         }
-        const float4 s = HAS_FLOW ? *reinterpret_cast<const float4*>(sGF2 + p * csp + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float sv[4] = {s.x, s.y, s.z, s.w};
+        const float4 sc = HAS_FLOW ? *reinterpret_cast<const float4*>(sGF2 + p * csp + 4 * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float sv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (4 * q4 + k < nch) {
