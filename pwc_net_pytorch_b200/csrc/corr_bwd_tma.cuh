@@ -42,7 +42,7 @@ struct BwdTmaCfg {
     static constexpr int WP = HWD + 4;                      // X tile pitch (TMA box width), 4 mod 8
     static constexpr int PP = TW + 4;                       // partial-slice pitch, 4 mod 8
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 8;                            // X-chunk ring: deep enough to cover the TMA latency
+    static constexpr int NS = 5;                            // X-chunk ring: deep enough to cover the TMA latency
     static constexpr int X_ELEMS = CK * HH * WP;
     static constexpr int SLICE_ELEMS = CK * TH * PP;        // one warp's partial sums for one chunk
     static constexpr int PART_ELEMS = D * SLICE_ELEMS;
@@ -174,29 +174,50 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const float* gon = gout + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W;
             const float* gaten = gate ? gate + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W
                                       : nullptr;
+            // phase 1: every aligned quad this thread needs, all requests in flight together (one L2 round
+            // trip per tile instead of one per displacement column)
+            constexpr int NQ = 3;
+            float4 raw[D][NQ];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
                 const int sh = ((-dx) % 4 + 4) % 4;            // (xs - dx) mod 4, compile time
                 const int xb = xs - dx - sh;                   // aligned start
-                constexpr int NQ = 3;
-                float t[4 * NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     const int x = xb + 4 * q;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W) {
-                        v = __ldg(reinterpret_cast<const float4*>(gon + (size_t)d * HW + x));
-                        if (gaten) {   // leaky_relu_ backward, model.py:84: gate by the sign of the forward output
+                    raw[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W)
+                        raw[d][q] = __ldg(reinterpret_cast<const float4*>(gon + (size_t)d * HW + x));
+                }
+            }
+            // phase 2 (only with the LeakyReLU gate, model.py:84): scale by the sign of the forward output
+            if (gaten) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
+                    const int sh = ((-dx) % 4 + 4) % 4;
+                    const int xb = xs - dx - sh;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int x = xb + 4 * q;
+                        if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W) {
                             const float4 o = __ldg(reinterpret_cast<const float4*>(gaten + (size_t)d * HW + x));
-                            if (o.x < 0.0f) v.x *= slope;
-                            if (o.y < 0.0f) v.y *= slope;
-                            if (o.z < 0.0f) v.z *= slope;
-                            if (o.w < 0.0f) v.w *= slope;
+                            if (o.x < 0.0f) raw[d][q].x *= slope;
+                            if (o.y < 0.0f) raw[d][q].y *= slope;
+                            if (o.z < 0.0f) raw[d][q].z *= slope;
+                            if (o.w < 0.0f) raw[d][q].w *= slope;
                         }
                     }
-                    t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
                 }
+            }
+            // phase 3: pick the 8 wanted values (compile-time shifts)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
+                const int sh = ((-dx) % 4 + 4) % 4;
+                const float t[4 * NQ] = {raw[d][0].x, raw[d][0].y, raw[d][0].z, raw[d][0].w, raw[d][1].x, raw[d][1].y,
+                                         raw[d][1].z, raw[d][1].w, raw[d][2].x, raw[d][2].y, raw[d][2].z, raw[d][2].w};
 #pragma unroll
                 for (int p = 0; p < PX; ++p) G[p][d] = (xs + p < W) ? t[sh + p] : 0.0f;
             }

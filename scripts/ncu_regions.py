@@ -1,9 +1,12 @@
 """Aggregates ncu warp-state samples of one kernel by code region (between sync/memory markers).
-usage: python scripts/ncu_regions.py file.ncu-rep [min_samples]"""
+usage: python scripts/ncu_regions.py file.ncu-rep [min_samples] [kernel_index]"""
 import csv, io, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, data = rows[1], rows[2:]
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rows = rows[starts[kidx]:starts[kidx + 1]]
+hdr, data = rows[1], [r for r in rows[2:] if len(r) > 5]
 ix = {h: i for i, h in enumerate(hdr)}
 mins = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 tot = sum(int(r[ix['# Samples']]) for r in data)
