@@ -10,11 +10,16 @@
 //
 // Persistent CTA (one per SM) walking 16x16 tiles; work item = (tile, chunk of CK channels).
 //   T  1 warp : TMA requests for the X tile + halo chunks (ring of NS).
+//   S  4 warps: stage the NEXT tile's output-gradient taps in shared memory with cp.async (16/8/4-byte
+//               copies from the shifted positions y-dy, x-dx, zero fill outside the image) while the
+//               consumers work on the current tile, so the taps never cost an exposed global round trip.
 //   C  9 warps: warp wd owns displacement row tj = wd - 4; lane (lr, ls) owns an 8-pixel strip and
-//               keeps its 8x9 output-gradient taps in registers for the whole tile (read once from
-//               global, LeakyReLU gate applied on the way); per channel 4 LDS.128 feed 72 FFMA and
+//               keeps its 8x9 output-gradient taps in registers for the whole tile (18 conflict-free
+//               LDS.128 from the staging buffer); per channel 4 LDS.128 feed 72 FFMA and
 //               leave 8 partial sums, written to the warp's own slice of a double-buffered
 //               partial-sum buffer (no atomics: the result is deterministic).
+//   The LeakyReLU gate (model.py:84) is applied to the output gradient by a separate elementwise pass
+//   (gate_grad_kernel) before these kernels run.
 //   R  2 warps: sum the 9 slices, scale by 1/C and store the gradient chunk (128-bit, full sectors).
 // Roles meet only through mbarriers.  Requires W % 4 == 0 and 16-byte aligned bases (TMA).
 #pragma once
@@ -31,13 +36,33 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int x, i
                  : "memory");
 }
 
+// Ampere-style asynchronous copy global -> shared of BYTES (4, 8 or 16) per lane; src_bytes == 0 writes zeros.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES), "r"(src_bytes)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Tap staging buffer: [81][16 rows][16 px], the four 16-byte chunks of a row XOR-swizzled with
+// (row >> 1) & 3, so that the consumers' LDS.128 (8 rows x one chunk per quarter warp) are conflict-free.
+__device__ __forceinline__ int tap_slot(int d, int row, int x)
+{
+    return d * 256 + row * 16 + ((((x >> 2) ^ (row >> 1)) & 3) << 2) + (x & 3);
+}
+
 template <int S2_, int CK_>
 struct BwdTmaCfg {
     static constexpr int D = 9, S2 = S2_, CK = CK_, PX = 8;
     static constexpr int r = 4, R = r * S2;
     static constexpr int TW = 16, TH = 16;
-    static constexpr int NCONS = 32 * D, NRED = 64;
-    static constexpr int NT = NCONS + NRED + 32;            // 12 warps
+    static constexpr int NCONS = 32 * D, NRED = 64, NSTAGE = 128;
+    static constexpr int NT = NCONS + NRED + 32 + NSTAGE;   // 16 warps: C 9, R 2, T 1, S 4 (128 registers each)
     static constexpr int HH = TH + 2 * R, HWD = TW + 2 * R;
     static constexpr int WP = HWD + 4;                      // X tile pitch (TMA box width), 4 mod 8
     static constexpr int PP = TW + 4;                       // partial-slice pitch, 4 mod 8
@@ -48,19 +73,19 @@ struct BwdTmaCfg {
     static constexpr int PART_ELEMS = D * SLICE_ELEMS;
     static constexpr uint32_t X_BYTES = X_ELEMS * 4;
     static constexpr int CTRL_BYTES = 256;
+    static constexpr int TAP_ELEMS = D * D * TH * TW;       // staged output-gradient taps of one tile
     static constexpr int GBOX_C = 27;                       // gradient-tap prefetch box: 27 of the 81 channels
     static_assert(WP % 8 == 4 && PP % 8 == 4, "pitches must be 4 mod 8 floats");
     static_assert(X_BYTES % 128 == 0 && (PART_ELEMS * 4) % 128 == 0, "buffers stay 128B aligned");
-    static_assert((2 * NS + 4) * 8 <= CTRL_BYTES, "control block too small");
-    static constexpr size_t smem_bytes() { return CTRL_BYTES + (size_t)NS * X_BYTES + 2 * (size_t)PART_ELEMS * 4; }
+    static_assert((2 * NS + 6) * 8 <= CTRL_BYTES, "control block too small");
+    static constexpr size_t smem_bytes() { return CTRL_BYTES + (size_t)NS * X_BYTES + 2 * (size_t)PART_ELEMS * 4 + (size_t)TAP_ELEMS * 4; }
 };
 
 template <class Cfg, int SIGN>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
-                    const float* __restrict__ gout,
-                    const float* __restrict__ gate, float* __restrict__ res,
-                    int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float slope)
+                    const float* __restrict__ gout, float* __restrict__ res,
+                    int C, int H, int W, int tiles_x, int tiles_y, int ntiles)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, WP = Cfg::WP, PP = Cfg::PP;
@@ -71,8 +96,11 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint64_t* barEmpty = barFull + NS;                       // [NS] X chunk consumed           (C -> T)
     uint64_t* barPart = barEmpty + NS;                       // [2]  partial sums written       (C -> R)
     uint64_t* barPartFree = barPart + 2;                     // [2]  partial sums read          (R -> C)
+    uint64_t* barTap = barPartFree + 2;                      // [1]  taps of a tile staged      (T cp.async -> C)
+    uint64_t* barTapFree = barTap + 1;                       // [1]  taps copied to registers   (C -> T)
     float* sX = reinterpret_cast<float*>(base + Cfg::CTRL_BYTES);
     float* sPart = sX + NS * Cfg::X_ELEMS;                   // [2][D][CK][TH][PP]
+    float* sTap = sPart + 2 * Cfg::PART_ELEMS;               // [81][TH][TW] swizzled (tap_slot)
 
     const int tid = threadIdx.x;
     const size_t HW = (size_t)H * W;
@@ -91,9 +119,58 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_init(&barPart[i], NCONS);
             mbar_init(&barPartFree[i], NRED);
         }
+        mbar_init(barTap, Cfg::NSTAGE);
+        mbar_init(barTapFree, NCONS);
         fence_mbar_init();
     }
     __syncthreads();
+
+    if (tid >= NCONS + NRED + 32) {
+        // ================================ S: tap staging ================================
+        const int lane = tid & 31, sw = (tid - (NCONS + NRED + 32)) >> 5;      // sw: 0..3, owns rows dyi = sw, sw+4, sw+8
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+            if (lt >= 1) mbar_wait(barTapFree, (lt - 1) & 1);      // tile lt-1's taps are in the consumers' registers
+            const float* gon = gout + (size_t)tc.n * (D * D) * HW;
+            for (int dyi = sw; dyi < D; dyi += 4) {
+                const int dy = (SIGN > 0) ? 0 : (dyi - 4) * S2;
+#pragma unroll
+                for (int dxi = 0; dxi < D; ++dxi) {
+                    const int dx = (SIGN > 0) ? 0 : (dxi - 4) * S2;
+                    const int d = dyi * D + dxi;
+                    const float* plane = gon + (size_t)d * HW;
+                    // widest copy the shift allows (tile rows start on multiples of 16 pixels)
+                    if (dx % 4 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int i = lane + 32 * j, row = i >> 2, x = (i & 3) * 4;
+                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
+                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W % 4 == 0: whole quads
+                            cp_async_zfill<16>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 16 : 0);
+                        }
+                    } else if (dx % 2 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = lane + 32 * j, row = i >> 3, x = (i & 7) * 2;
+                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
+                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W is even: whole pairs
+                            cp_async_zfill<8>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 8 : 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int i = lane + 32 * j, row = i >> 4, x = i & 15;
+                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
+                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;
+                            cp_async_zfill<4>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 4 : 0);
+                        }
+                    }
+                }
+            }
+            cp_async_mbar_arrive(barTap);       // arrives once this thread's copies have landed
+        }
+        return;
+    }
 
     if (tid >= NCONS + NRED) {
         // ================================ T: TMA issue ================================
@@ -103,10 +180,10 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int g = 0; g < total; ++g) {
             const int s = g % NS;
             const TileCoord tc = tile_coord(blockIdx.x + (g / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
-            if (g % nchunks == 0 && g / nchunks + 1 < my_tiles) {
-                // first chunk of a tile: pull the NEXT tile's output-gradient taps into L2, so that the
-                // consumers' per-tile tap loads (their only global loads) hit L2 instead of DRAM
-                const TileCoord tn = tile_coord(blockIdx.x + (g / nchunks + 1) * gridDim.x, tiles_x, tiles_y, TH, TW);
+            if (g % nchunks == 0 && g / nchunks + 2 < my_tiles) {
+                // pull the output-gradient region of the tile after next into L2 (TMA prefetch, no shared
+                // memory): the S warps copy it one tile ahead of the consumers
+                const TileCoord tn = tile_coord(blockIdx.x + (g / nchunks + 2) * gridDim.x, tiles_x, tiles_y, TH, TW);
                 const int off = (SIGN > 0) ? 0 : R;
 #pragma unroll
                 for (int j = 0; j < (D * D) / Cfg::GBOX_C; ++j)
@@ -160,68 +237,19 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int rowsel = (SIGN > 0) ? wd : (D - 1 - wd);     // X row offset inside the halo tile, in units of S2
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
-        const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
         // ---- this thread's 8 x 9 output-gradient taps (registers for the whole tile) ----
+        // G[p][d] = gO[n, wd*9+d, y, xs+p] (SIGN > 0) or gO[n, wd*9+d, y-dy, xs+p-dx] (SIGN < 0), zero outside
+        // the image: staged by the T warp, already shifted, so both signs read the same two quads per d.
         float G[PX][D];
-        {
-            // 128-bit loads: a strip starts on a multiple of 8 pixels and W % 4 == 0, so every aligned
-            // quad is entirely inside or outside the row.  For SIGN < 0 the 8 wanted values start at
-            // xs - dx; they are picked out of 2 or 3 aligned quads with compile-time indices.
-            const int y = tc.y0 + lr, xs = tc.x0 + ls * PX;
-            const int dy = (wd - 4) * S2;
-            const int gy = (SIGN > 0) ? y : y - dy;
-            const bool row_ok = (y < H) && gy >= 0 && gy < H;
-            const float* gon = gout + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W;
-            const float* gaten = gate ? gate + (size_t)tc.n * (D * D) * HW + (size_t)(wd * D) * HW + (size_t)(row_ok ? gy : 0) * W
-                                      : nullptr;
-            // phase 1: every aligned quad this thread needs, all requests in flight together (one L2 round
-            // trip per tile instead of one per displacement column)
-            constexpr int NQ = 3;
-            float4 raw[D][NQ];
+        mbar_wait(barTap, lt & 1);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
-                const int sh = ((-dx) % 4 + 4) % 4;            // (xs - dx) mod 4, compile time
-                const int xb = xs - dx - sh;                   // aligned start
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const int x = xb + 4 * q;
-                    raw[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W)
-                        raw[d][q] = __ldg(reinterpret_cast<const float4*>(gon + (size_t)d * HW + x));
-                }
-            }
-            // phase 2 (only with the LeakyReLU gate, model.py:84): scale by the sign of the forward output
-            if (gaten) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
-                    const int sh = ((-dx) % 4 + 4) % 4;
-                    const int xb = xs - dx - sh;
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int x = xb + 4 * q;
-                        if ((q < 2 || sh > 0) && row_ok && x >= 0 && x < W) {
-                            const float4 o = __ldg(reinterpret_cast<const float4*>(gaten + (size_t)d * HW + x));
-                            if (o.x < 0.0f) raw[d][q].x *= slope;
-                            if (o.y < 0.0f) raw[d][q].y *= slope;
-                            if (o.z < 0.0f) raw[d][q].z *= slope;
-                            if (o.w < 0.0f) raw[d][q].w *= slope;
-                        }
-                    }
-                }
-            }
-            // phase 3: pick the 8 wanted values (compile-time shifts)
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int dx = (SIGN > 0) ? 0 : (d - 4) * S2;
-                const int sh = ((-dx) % 4 + 4) % 4;
-                const float t[4 * NQ] = {raw[d][0].x, raw[d][0].y, raw[d][0].z, raw[d][0].w, raw[d][1].x, raw[d][1].y,
-                                         raw[d][1].z, raw[d][1].w, raw[d][2].x, raw[d][2].y, raw[d][2].z, raw[d][2].w};
-#pragma unroll
-                for (int p = 0; p < PX; ++p) G[p][d] = (xs + p < W) ? t[sh + p] : 0.0f;
-            }
+        for (int d = 0; d < D; ++d) {
+            const float4 a = *reinterpret_cast<const float4*>(sTap + tap_slot(wd * D + d, lr, ls * PX));
+            const float4 b = *reinterpret_cast<const float4*>(sTap + tap_slot(wd * D + d, lr, ls * PX + 4));
+            G[0][d] = a.x; G[1][d] = a.y; G[2][d] = a.z; G[3][d] = a.w;
+            G[4][d] = b.x; G[5][d] = b.y; G[6][d] = b.z; G[7][d] = b.w;
         }
+        // (barTapFree is signalled after the first chunk's partial sums are stored: see below)
 
         for (int k = 0; k < nchunks; ++k, ++g) {
             const int s = g % NS, pb = g & 1;
@@ -249,7 +277,6 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 }
             }
-            mbar_arrive(&barEmpty[s]);                         // X chunk consumed
             if (g >= 2) mbar_wait(&barPartFree[pb], ((g >> 1) - 1) & 1);   // R has read this buffer's previous use
             float* dst = sPart + pb * Cfg::PART_ELEMS + wd * Cfg::SLICE_ELEMS + lr * PP + ls * PX;
 #pragma unroll
@@ -258,6 +285,12 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 *reinterpret_cast<float4*>(dst + c * (TH * PP) + 4) = make_float4(part[c][4], part[c][5], part[c][6], part[c][7]);
             }
             mbar_arrive(&barPart[pb]);                         // release: this warp's slice of chunk g is written
+            // The "consumed" signals come only now, after the stores above: those depend (through the FFMAs)
+            // on every shared load of this chunk and on every tap register, so all of them have landed.
+            // An mbarrier arrive issued right behind a still-pending LDS can overtake it, and the next TMA /
+            // cp.async write then corrupts the value being read (measured: last LDS.128 of a chunk).
+            mbar_arrive(&barEmpty[s]);                         // X chunk consumed
+            if (k == 0) mbar_arrive(barTapFree);               // the tap staging buffer may be overwritten
         }
     }
 }

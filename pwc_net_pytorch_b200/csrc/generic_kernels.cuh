@@ -337,4 +337,22 @@ deinterleave4_kernel(const float* __restrict__ src4, float* __restrict__ dst, in
     }
 }
 
+// LeakyReLU backward (model.py:84) as a stand-alone pass: dst = grad_out * (out < 0 ? slope : 1).
+// Feeds the TMA correlation-backward kernels, whose taps are staged by asynchronous copies and cannot
+// be gated on the way.  n4 = number of float4 elements.
+__global__ void __launch_bounds__(256)
+gate_grad_kernel(const float4* __restrict__ gout, const float4* __restrict__ out, float4* __restrict__ dst,
+                 size_t n4, float slope)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 g = __ldg(gout + i);
+    const float4 o = __ldg(out + i);
+    if (o.x < 0.0f) g.x *= slope;
+    if (o.y < 0.0f) g.y *= slope;
+    if (o.z < 0.0f) g.z *= slope;
+    if (o.w < 0.0f) g.w *= slope;
+    dst[i] = g;
+}
+
 }  // namespace pwc

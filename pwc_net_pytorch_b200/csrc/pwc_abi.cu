@@ -358,8 +358,7 @@ int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, f
 
 // returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
 template <int S2, int CK, int SIGN>
-int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* res,
-                   const pwc::CorrGeom& g, float slope, cudaStream_t st)
+int launch_bwd_tma(const float* gout, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
 {
     using Cfg = pwc::BwdTmaCfg<S2, CK>;
     CUtensorMap mX, mG;
@@ -385,7 +384,7 @@ int launch_bwd_tma(const float* gout, const float* gate, const float* X, float* 
     if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         sm_count = 148;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
-    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, gate, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, slope);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles);
     return check_launch("corr_bwd_tma_kernel");
 }
 
@@ -400,8 +399,12 @@ int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float
 
 // g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
 // which: 1 = g1 only, 2 = g2 only, 3 = both
+// gated_scratch (optional, B*81*H*W floats, 16-byte aligned): room for the LeakyReLU-gated output
+// gradient; without it a gated backward stays on the plain tiled kernels.  *gated_done tells a caller
+// that splits the two gradients over two calls that the scratch already holds the gated gradient.
 int corr_backward_impl(const float* gout, const float* gate, const float* f1, const float* second,
-                       float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st, int which = 3)
+                       float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st, int which = 3,
+                       float* gated_scratch = nullptr, bool* gated_done = nullptr)
 {
     if (g.s1 != 1)
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
@@ -412,14 +415,27 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
     if (fast_path(g)) {
         const float* any_in = second ? second : f1;
         float* any_out = g1 ? g1 : g2;
-        if (tma_eligible(f1, any_in, any_out, g) && (((uintptr_t)g2 | (uintptr_t)g1 | (uintptr_t)gout) & 15) == 0) {
+        const bool gate_ok = !gate || (gated_scratch && (((uintptr_t)gate | (uintptr_t)gated_scratch) & 15) == 0);
+        if (gate_ok && tma_eligible(f1, any_in, any_out, g) && (((uintptr_t)g2 | (uintptr_t)g1 | (uintptr_t)gout) & 15) == 0) {
+            const float* go = gout;
+            if (gate) {      // LeakyReLU backward as its own pass (the TMA kernels stage raw taps)
+                if (!gated_done || !*gated_done) {
+                    const size_t n4 = (size_t)g.B * g.oc * g.H * g.W / 4;      // W % 4 == 0 on this path
+                    pwc::gate_grad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+                        reinterpret_cast<const float4*>(gout), reinterpret_cast<const float4*>(gate),
+                        reinterpret_cast<float4*>(gated_scratch), n4, slope);
+                    if (!check_launch("gate_grad_kernel")) return 0;
+                    if (gated_done) *gated_done = true;
+                }
+                go = gated_scratch;
+            }
             int r1 = 1, r2 = 1;
             if (g.s2 == 1) {
-                if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(gout, gate, second, g1, g, slope, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(gout, gate, f1, g2, g, slope, st);
+                if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(go, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
             } else {
-                if (which & 1) r1 = launch_bwd_tma<2, 2, +1>(gout, gate, second, g1, g, slope, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<2, 2, -1>(gout, gate, f1, g2, g, slope, st);
+                if (which & 1) r1 = launch_bwd_tma<2, 2, +1>(go, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<2, 2, -1>(go, f1, g2, g, st);
             }
             if (r1 == 0 || r2 == 0) return 0;
             if (r1 > 0 && r2 > 0) return 1;
@@ -534,8 +550,8 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
                                           int, int)
 {
     if (!has_flow) return 0;
-    // warped second operand + its gradient + the 4-channel-interleaved scatter scratch
-    return (long long)sizeof(float) * (2LL * B * C * H * W + 4LL * B * ((C + 3) / 4) * H * W);
+    // warped second operand + its gradient + the 4-channel-interleaved scatter scratch + the gated output gradient
+    return (long long)sizeof(float) * (2LL * B * C * H * W + 4LL * B * ((C + 3) / 4) * H * W + 81LL * B * H * W);
 }
 
 int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
@@ -562,24 +578,27 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     float* wbuf = static_cast<float*>(workspace);
     float* gwarped = wbuf + N;
     float* scratch = gwarped + N;
+    float* gated = scratch + 4 * (size_t)B * ((C + 3) / 4) * H * W;      // used only with act on the TMA kernels
+    if (g.oc != 81) gated = nullptr;                                     // (sized for the 81-displacement fast path)
+    bool gated_done = false;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
     const bool split_ok = fast_path(g);      // the tiled kernels compute the two gradients in separate launches
     if (vec_ok && split_ok) {
         // 1. gradient w.r.t. the warped features (needs f1 and grad_out only)
-        if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2)) return 0;
+        if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2, gated, &gated_done)) return 0;
         // 2. scatter to grad_f2 + flow gradient; the same pass re-materialises x2_warp when the forward did
         //    not export it (both need the four bilinear corner values)
         if (!warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, warped_in ? nullptr : wbuf, B, C, H, W, stream))
             return 0;
         // 3. gradient w.r.t. f1 (needs x2_warp)
-        return corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1);
+        return corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1, gated, &gated_done);
     }
     const float* warped = warped_in;
     if (!warped) {      // re-materialise x2_warp (the forward never stored it)
         if (!pwc_warp_forward(f2, flow, wbuf, B, C, H, W, stream)) return 0;
         warped = wbuf;
     }
-    if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream)) return 0;
+    if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream, 3, gated, &gated_done)) return 0;
     if (vec_ok) return warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, nullptr, B, C, H, W, stream);
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
 }

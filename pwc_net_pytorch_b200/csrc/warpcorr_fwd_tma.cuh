@@ -111,7 +111,7 @@ struct TmaCfg {
     static constexpr int PXB = (NHALO + NBIL - 1) / NBIL;  // halo pixels per bilinear thread
     static constexpr int PXP = (NHALO + 31) / 32;          // halo pixels per lane of the taps warp
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 4;                           // warped-chunk ring (B -> C); 6 measured identical
+    static constexpr int NS = 5;                           // warped-chunk ring (B -> C); a slot is released one chunk late (see C)
     static constexpr int NF1 = 8;                          // f1 ring
     static constexpr int NWIN = 3;                         // f2 window ring (T -> B)
     static constexpr int WIN_ELEMS = CK * WH * WW;
@@ -469,6 +469,11 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
 #pragma unroll
             for (int d = 0; d < D; ++d) acc[p][d] = 0.0f;
 
+        // A chunk's "consumed" signals are given one loop iteration late (or after the epilogue stores for
+        // the last chunk of a tile): an mbarrier arrive issued right behind a still-pending LDS can overtake
+        // it, and the producer's next write then corrupts the value being read (measured in corr_bwd_tma.cuh).
+        // One iteration later every instruction of the chunk has issued, so all its loads have landed.
+#pragma unroll 1
         for (int k = 0; k < nchunks; ++k, ++g) {
             const int s = g % NS, sf = g % NF1;
             mbar_wait(&barF1[sf], (g / NF1) & 1);
@@ -519,8 +524,10 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                     for (int p = 0; p < PX; ++p) f[p] = fn[p];
                 }
             }
-            mbar_arrive(&barEmpty[s]);       // warped chunk slot s consumed
-            mbar_arrive(&barF1Free[sf]);     // f1 chunk slot sf consumed
+            if (k > 0) {
+                mbar_arrive(&barEmpty[(g - 1) % NS]);       // warped chunk slot of the previous chunk consumed
+                mbar_arrive(&barF1Free[(g - 1) % NF1]);     // f1 chunk slot of the previous chunk consumed
+            }
         }
 
         // ---- epilogue: 1/C, optional LeakyReLU (model.py:84) ----
@@ -545,6 +552,10 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                 }
             }
         }
+        // last chunk of the tile: its loads fed the accumulators that were just stored (threads outside the
+        // image store nothing, but they are a whole epilogue past the loads as well)
+        mbar_arrive(&barEmpty[(g - 1) % NS]);
+        mbar_arrive(&barF1Free[(g - 1) % NF1]);
     }
 }
 

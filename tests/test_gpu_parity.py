@@ -390,7 +390,8 @@ def test_unaligned_buffers_through_the_c_abi():
     a, b, f, g = (shifted(x) for x in (f1, f2, flow, go))
     out = shifted(np.zeros((2, 81, 16, 24), np.float32))
     g1, g2, gf = (shifted(np.zeros_like(x)) for x in (f1, f2, flow))
-    ws = torch.empty(2 * f1.size + 4 * 2 * 2 * 16 * 24 + 1, device=dev())[1:]
+    need = L.pwc_warpcorr_backward_workspace(2, 6, 16, 24, 1, 4, 1, 4, 1, 1)
+    ws = torch.empty(need // 4 + 1, device=dev())[1:]
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     assert all(t.data_ptr() % 16 == 4 for t in (a, b, f, g, out, g1, g2, gf))
