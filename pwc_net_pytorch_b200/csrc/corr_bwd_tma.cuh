@@ -10,7 +10,7 @@
 //
 // Persistent CTA (one per SM) walking 16x16 tiles; work item = (tile, chunk of CK channels).
 //   T  1 warp : TMA requests for the X tile + halo chunks (ring of NS).
-//   S  4 warps: stage the NEXT tile's output-gradient taps in shared memory with cp.async (16/8/4-byte
+//   S  3 warps: stage the NEXT tile's output-gradient taps in shared memory with cp.async (16/8/4-byte
 //               copies from the shifted positions y-dy, x-dx, zero fill outside the image) while the
 //               consumers work on the current tile, so the taps never cost an exposed global round trip.
 //   C  9 warps: warp wd owns displacement row tj = wd - 4; lane (lr, ls) owns an 8-pixel strip and
@@ -20,7 +20,7 @@
 //               partial-sum buffer (no atomics: the result is deterministic).
 //   The LeakyReLU gate (model.py:84) is applied to the output gradient by a separate elementwise pass
 //   (gate_grad_kernel) before these kernels run.
-//   R  2 warps: sum the 9 slices, scale by 1/C and store the gradient chunk (128-bit, full sectors).
+//   R  3 warps: sum the 9 slices, scale by 1/C and store the gradient chunk (128-bit, full sectors).
 // Roles meet only through mbarriers.  Requires W % 4 == 0 and 16-byte aligned bases (TMA).
 #pragma once
 #include "warpcorr_fwd_tma.cuh"
@@ -61,8 +61,8 @@ struct BwdTmaCfg {
     static constexpr int D = 9, S2 = S2_, CK = CK_, PX = 8;
     static constexpr int r = 4, R = r * S2;
     static constexpr int TW = 16, TH = 16;
-    static constexpr int NCONS = 32 * D, NRED = 64, NSTAGE = 128;
-    static constexpr int NT = NCONS + NRED + 32 + NSTAGE;   // 16 warps: C 9, R 2, T 1, S 4 (128 registers each)
+    static constexpr int NCONS = 32 * D, NRED = 96, NSTAGE = 96;
+    static constexpr int NT = NCONS + NRED + 32 + NSTAGE;   // 16 warps: C 9, R 3, T 1, S 3 (128 registers each)
     static constexpr int HH = TH + 2 * R, HWD = TW + 2 * R;
     static constexpr int WP = HWD + 4;                      // X tile pitch (TMA box width), 4 mod 8
     static constexpr int PP = TW + 4;                       // partial-slice pitch, 4 mod 8
@@ -127,12 +127,12 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     if (tid >= NCONS + NRED + 32) {
         // ================================ S: tap staging ================================
-        const int lane = tid & 31, sw = (tid - (NCONS + NRED + 32)) >> 5;      // sw: 0..3, owns rows dyi = sw, sw+4, sw+8
+        const int lane = tid & 31, sw = (tid - (NCONS + NRED + 32)) >> 5;      // sw: 0..2, owns rows dyi = sw, sw+3, sw+6
         for (int lt = 0; lt < my_tiles; ++lt) {
             const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
             if (lt >= 1) mbar_wait(barTapFree, (lt - 1) & 1);      // tile lt-1's taps are in the consumers' registers
             const float* gon = gout + (size_t)tc.n * (D * D) * HW;
-            for (int dyi = sw; dyi < D; dyi += 4) {
+            for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32) {
                 const int dy = (SIGN > 0) ? 0 : (dyi - 4) * S2;
 #pragma unroll
                 for (int dxi = 0; dxi < D; ++dxi) {

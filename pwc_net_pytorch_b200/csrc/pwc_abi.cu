@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "corr_bwd.cuh"
+#include "corr_bwd_seq.cuh"
 #include "corr_bwd_tma.cuh"
 #include "generic_kernels.cuh"
 #include "pwc_common.cuh"
@@ -22,6 +23,7 @@ std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_generic{0};
 std::atomic<int> g_disable_tma{0};
 std::atomic<int> g_disable_small{0};
+std::atomic<int> g_disable_seq{0};
 
 int fail(const char* fmt, ...)
 {
@@ -388,6 +390,36 @@ int launch_bwd_tma(const float* gout, const float* X, float* res, const pwc::Cor
     return check_launch("corr_bwd_tma_kernel");
 }
 
+// stride2 == 1: threads own complete outputs (corr_bwd_seq.cuh).  returns 1 ok, 0 error, -1 "not taken"
+template <int SIGN>
+int launch_bwd_seq(const float* gout, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
+{
+    using Cfg = pwc::BwdSeqCfg;
+    CUtensorMap mX, mG;
+    if (!make_nchw_map(&mX, X, g.B, g.C, g.H, g.W, Cfg::WP, Cfg::HH, Cfg::CPI)) return -1;
+    if (!make_nchw_map(&mG, gout, g.B, 81, g.H, g.W, SIGN > 0 ? Cfg::TW : Cfg::HWD, SIGN > 0 ? Cfg::TH : Cfg::HH,
+                       Cfg::GBOX_C))
+        return -1;
+    auto kern = pwc::corr_bwd_seq_kernel<SIGN>;
+    const size_t smem = Cfg::smem_bytes();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+        configured_dev = dev;
+    }
+    const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
+    const int nsc = pwc::cdiv(g.C, Cfg::CPI);
+    const long long nitems = (long long)tiles_x * tiles_y * g.B * nsc;
+    if (nitems > 0x3fffffffLL) return fail("grid too large");
+    const int sms = sm_count_of_current_device();
+    const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)nitems, nsc);
+    return check_launch("corr_bwd_seq_kernel");
+}
+
 template <int S2, int SIGN>
 int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float* res,
                      const pwc::CorrGeom& g, float slope, cudaStream_t st)
@@ -430,7 +462,13 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
                 go = gated_scratch;
             }
             int r1 = 1, r2 = 1;
-            if (g.s2 == 1) {
+            if (g.s2 == 1 && !g_disable_seq.load()) {
+                // g1: threads own complete outputs (90 vs 111 us at the level-2 shape).  The gradient w.r.t. the
+                // second operand stays on the slice/reduce kernel: its taps sit at shifted, 4-byte aligned
+                // positions, and streaming them row by row costs more than the reducer it saves (124 vs 113 us).
+                if (which & 1) r1 = launch_bwd_seq<+1>(go, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
+            } else if (g.s2 == 1) {
                 if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(go, second, g1, g, st);
                 if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
             } else {
