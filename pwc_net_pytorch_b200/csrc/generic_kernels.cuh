@@ -337,6 +337,117 @@ deinterleave4_kernel(const float* __restrict__ src4, float* __restrict__ dst, in
     }
 }
 
+// Same scatter with an 8-channel interleave: scratch [B][ceil(C/8)][H][W][8] (zeroed by the caller).
+// Two adjacent lanes own the two channel quads of one (pixel, channel octet), so their two
+// red.global.add.v4.f32 fall into the SAME 32-byte sector: the LSU issues one sector request per lane
+// pair instead of one per lane (the scatter is bound by those requests: 64% of its L1 wavefronts were
+// reduction sectors with the 4-channel layout).  The pair also sums its flow-gradient terms with one
+// shuffle before the atomic.  One thread per (n, channel octet, y, x, half).
+__global__ void __launch_bounds__(256)
+warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
+                   const float* __restrict__ flow, float* __restrict__ gx8,
+                   float* __restrict__ gflow, float* __restrict__ warped_out, int B, int C, int H, int W, int cocts)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t total = (size_t)B * HW * cocts * 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;                         // total is even: a lane pair is in or out together
+    const int half = (int)(idx & 1);
+    const size_t pidx = idx >> 1;
+    const size_t pix = pidx % HW;
+    const int co = (int)((pidx / HW) % cocts);
+    const int n = (int)(pidx / (HW * cocts));
+    const int cq = 2 * co + half;                     // this lane's channel quad
+    const int yy = (int)(pix / W), xx = (int)(pix % W);
+    const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
+    const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
+    float ax = 0.0f, ay = 0.0f;
+    int x0 = 0, y0 = 0;
+    const Tap t = make_tap(xx, yy, u, v, H, W, &ax, &ay, &x0, &y0);
+    if (t.off < 0) {                // nothing to scatter, zero flow gradient (the buffers are zeroed)
+        if (warped_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (4 * cq + k < C) warped_out[((size_t)n * C + 4 * cq + k) * HW + pix] = 0.0f;
+        }
+        return;
+    }
+    const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
+    const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
+    const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;
+    float g[4];
+    float gu = 0.0f, gv = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = 4 * cq + k;
+        g[k] = 0.0f;
+        if (c < C) {
+            const size_t plane = ((size_t)n * C + c) * HW;
+            g[k] = __ldg(gout + plane + pix);
+            const float* p = x + plane + t.off;
+            const float v00 = m00 * __ldg(p), v01 = m01 * __ldg(p + t.dx);
+            const float v10 = m10 * __ldg(p + t.dyw), v11 = m11 * __ldg(p + t.dyw + t.dx);
+            gu = fmaf(g[k], fmaf(v11 - v10, ay, (v01 - v00) * (1.0f - ay)), gu);
+            gv = fmaf(g[k], fmaf(v11 - v01, ax, (v10 - v00) * (1.0f - ax)), gv);
+            if (warped_out)   // same expression as tap_sample (weights of masked corners are 0)
+                warped_out[plane + pix] = fmaf(t.w11, v11, fmaf(t.w10, v10, fmaf(t.w01, v01, t.w00 * v00)));
+        }
+    }
+    if (gx8 && 4 * cq < C) {
+        float* q = gx8 + (((size_t)n * cocts + co) * HW + t.off) * 8 + 4 * half;
+        const size_t sdx = (size_t)t.dx * 8, sdy = (size_t)t.dyw * 8;
+        if (t.w00 != 0.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(g[0] * t.w00), "f"(g[1] * t.w00),
+                         "f"(g[2] * t.w00), "f"(g[3] * t.w00) : "memory");
+        if (t.w01 != 0.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdx), "f"(g[0] * t.w01), "f"(g[1] * t.w01),
+                         "f"(g[2] * t.w01), "f"(g[3] * t.w01) : "memory");
+        if (t.w10 != 0.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdy), "f"(g[0] * t.w10), "f"(g[1] * t.w10),
+                         "f"(g[2] * t.w10), "f"(g[3] * t.w10) : "memory");
+        if (t.w11 != 0.0f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdy + sdx), "f"(g[0] * t.w11),
+                         "f"(g[1] * t.w11), "f"(g[2] * t.w11), "f"(g[3] * t.w11) : "memory");
+    }
+    if (gflow) {
+        // the two lanes of a pair took the same path up to here (same pixel, same tap)
+        const unsigned mask = __activemask();
+        gu += __shfl_xor_sync(mask, gu, 1);
+        gv += __shfl_xor_sync(mask, gv, 1);
+        if (half == 0) {
+            float* gf = gflow + (size_t)n * 2 * HW + pix;
+            if (cocts == 1) {
+                gf[0] = gu;
+                gf[HW] = gv;
+            } else {
+                atomicAdd(gf, gu);
+                atomicAdd(gf + HW, gv);
+            }
+        }
+    }
+}
+
+// [B][ceil(C/8)][H][W][8] scratch -> NCHW gradient (fully overwrites the destination).
+__global__ void __launch_bounds__(256)
+deinterleave8_kernel(const float* __restrict__ src8, float* __restrict__ dst, int B, int C, int H, int W, int cocts)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t total = (size_t)B * HW * cocts;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t pix = idx % HW;
+    const int co = (int)((idx / HW) % cocts);
+    const int n = (int)(idx / (HW * cocts));
+    const float4* s = reinterpret_cast<const float4*>(src8) + (((size_t)n * cocts + co) * HW + pix) * 2;
+    const float4 a = __ldg(s), b = __ldg(s + 1);
+    const float vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = 8 * co + k;
+        if (c < C) dst[((size_t)n * C + c) * HW + pix] = vals[k];
+    }
+}
+
 // LeakyReLU backward (model.py:84) as a stand-alone pass: dst = grad_out * (out < 0 ? slope : 1).
 // Feeds the TMA correlation-backward kernels, whose taps are staged by asynchronous copies and cannot
 // be gated on the way.  n4 = number of float4 elements.

@@ -489,23 +489,23 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
     return check_launch("corr_bwd_generic_kernel");
 }
 
-// Feature-gradient scatter through the 4-channel-interleaved scratch (see warp_bwd_v4_kernel).
-// scratch holds B * ceil(C/4) * H * W * 4 floats, 16-byte aligned.
+// Feature-gradient scatter through the 8-channel-interleaved scratch (see warp_bwd_v8_kernel).
+// scratch holds B * ceil(C/8) * H * W * 8 floats, 16-byte aligned.
 int warp_backward_v4(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
                      float* scratch, float* warped_out, int B, int C, int H, int W, cudaStream_t stream)
 {
-    const int cquads = pwc::cdiv(C, 4);
-    const size_t n4 = (size_t)B * cquads * H * W * 4;
-    if (cudaMemsetAsync(scratch, 0, sizeof(float) * n4, stream) != cudaSuccess)
+    const int cocts = pwc::cdiv(C, 8);
+    const size_t n8 = (size_t)B * cocts * H * W * 8;
+    if (cudaMemsetAsync(scratch, 0, sizeof(float) * n8, stream) != cudaSuccess)
         return fail("cudaMemsetAsync(scratch): %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)
         return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
-    const size_t total = (size_t)B * H * W * cquads;
-    pwc::warp_bwd_v4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow,
-                                                                                warped_out, B, C, H, W, cquads);
-    if (!check_launch("warp_bwd_v4_kernel")) return 0;
-    pwc::deinterleave4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cquads);
-    return check_launch("deinterleave4_kernel");
+    const size_t total = (size_t)B * H * W * cocts;
+    pwc::warp_bwd_v8_kernel<<<(unsigned)((2 * total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow,
+                                                                                    warped_out, B, C, H, W, cocts);
+    if (!check_launch("warp_bwd_v8_kernel")) return 0;
+    pwc::deinterleave8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cocts);
+    return check_launch("deinterleave8_kernel");
 }
 
 }  // namespace
@@ -588,8 +588,8 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
                                           int, int)
 {
     if (!has_flow) return 0;
-    // warped second operand + its gradient + the 4-channel-interleaved scatter scratch + the gated output gradient
-    return (long long)sizeof(float) * (2LL * B * C * H * W + 4LL * B * ((C + 3) / 4) * H * W + 81LL * B * H * W);
+    // warped second operand + its gradient + the 8-channel-interleaved scatter scratch + the gated output gradient
+    return (long long)sizeof(float) * (2LL * B * C * H * W + 8LL * B * ((C + 7) / 8) * H * W + 81LL * B * H * W);
 }
 
 int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
@@ -616,7 +616,7 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     float* wbuf = static_cast<float*>(workspace);
     float* gwarped = wbuf + N;
     float* scratch = gwarped + N;
-    float* gated = scratch + 4 * (size_t)B * ((C + 3) / 4) * H * W;      // used only with act on the TMA kernels
+    float* gated = scratch + 8 * (size_t)B * ((C + 7) / 8) * H * W;      // used only with act on the TMA kernels
     if (g.oc != 81) gated = nullptr;                                     // (sized for the 81-displacement fast path)
     bool gated_done = false;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
