@@ -138,6 +138,9 @@ int pwc_set_disable_tma(int on);
 /* disables the whole-image kernels of the coarse pyramid levels (H*W <= 256), so that the tiled
  * kernels serve those shapes too; test hook, returns the previous value. */
 int pwc_set_disable_small(int on);
+/* disables the complete-output kernel of the gradient w.r.t. input1 (corr_bwd_seq_kernel), so that the
+ * slice/reduce kernel serves stride2 == 1 too; test hook, returns the previous value. */
+int pwc_set_disable_seq(int on);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ EXPORTS = (
     "pwc_set_force_generic",
     "pwc_set_disable_tma",
     "pwc_set_disable_small",
+    "pwc_set_disable_seq",
 )
 
 
@@ -78,6 +79,8 @@ def _declare(L):
     L.pwc_set_disable_tma.restype = _int
     L.pwc_set_disable_small.argtypes = [_int]
     L.pwc_set_disable_small.restype = _int
+    L.pwc_set_disable_seq.argtypes = [_int]
+    L.pwc_set_disable_seq.restype = _int
 
 
 def load():

@@ -518,6 +518,7 @@ long long pwc_launch_count(void) { return g_launches.load(); }
 int pwc_set_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 int pwc_set_disable_tma(int on) { return g_disable_tma.exchange(on ? 1 : 0); }
 int pwc_set_disable_small(int on) { return g_disable_small.exchange(on ? 1 : 0); }
+int pwc_set_disable_seq(int on) { return g_disable_seq.exchange(on ? 1 : 0); }
 
 int pwc_corr_output_shape(int H, int W, int pad_size, int kernel_size, int max_displacement,
                           int stride1, int stride2, int* out_channels, int* out_h, int* out_w)

@@ -109,6 +109,7 @@ class Net(nn.Module):
         # optional leaky_relu_ of model.py:84 (slope 0.01) is the kernel's epilogue
         self.warp_corr = ops if ops is not None else FusedWarpCorrelation.from_search_range(
             args.search_range, activation=bool(args.corr_activation), negative_slope=0.01, return_warped=True)
+        self._own_ops = ops is None
         self._direct_concat = ops is None and args.search_range == 4
         self.flow_estimators = []
         for l, ch in enumerate(args.lv_chs[::-1] + [3]):
@@ -141,6 +142,9 @@ class Net(nn.Module):
             else:        # model.py:78: F.upsample(..., 'bilinear') == align_corners=False
                 flow = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=False) * 2
             # ---- hot path (model.py:80-84): one fused launch ----
+            # l == 0: the flow is identically zero, the warp is the identity (model.py:74-76 still runs it);
+            # the kernel is told so and skips taps, window and gather (x2_warp is then x2 itself, bit for bit)
+            wflow = None if (l == 0 and self._own_ops) else flow
             if self._direct_concat and not torch.is_grad_enabled():
                 # inference: the kernel writes the cost volume straight into the estimator's input
                 # [x1 | corr | flow] (model.py:89-91); torch.cat would copy its 81 channels once more
@@ -148,9 +152,9 @@ class Net(nn.Module):
                 est_in = torch.empty((x1.size(0), C + 81 + 2, x1.size(2), x1.size(3)), dtype=x1.dtype, device=x1.device)
                 est_in[:, :C] = x1
                 est_in[:, C + 81:] = flow
-                _, x2_warp = self.warp_corr(x1, x2, flow, out=est_in[:, C:C + 81])
+                _, x2_warp = self.warp_corr(x1, x2, wflow, out=est_in[:, C:C + 81])
             else:
-                corr, x2_warp = self.warp_corr(x1, x2, flow)
+                corr, x2_warp = self.warp_corr(x1, x2, wflow)
                 est_in = torch.cat([x1, corr, flow], dim=1)
             flow_coarse = self.flow_estimators[l](est_in)
             if args.residual:

@@ -552,3 +552,36 @@ def test_small_image_plain_correlation(shape, cfg):
     g1, g2 = co.corr_backward(go, f1, f2, *cfg)
     assert max_rel(a.grad.cpu().numpy(), g1) < TOL
     assert max_rel(b.grad.cpu().numpy(), g2) < TOL
+
+
+@pytest.mark.parametrize("shape", [(150, 8, 16, 32), (3, 40, 40, 44), (2, 70, 24, 28)])
+@pytest.mark.parametrize("act", [False, True])
+def test_seq_backward_equals_slice_backward_multi_tile(shape, act):
+    """stride2 == 1: the gradient w.r.t. f1 comes from corr_bwd_seq_kernel (threads own complete outputs);
+    with it switched off the slice/reduce kernel computes the same thing.  (150, 8, 16, 32) gives every
+    persistent CTA several tiles (the tap ring, the X double buffer and their release order matter
+    there), 40 and 70 channels exercise partial and multiple 32-channel items."""
+    B, C, H, W = shape
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=97)
+    go = rng.standard_normal((B, 81, H, W)).astype(np.float32)
+    L = _lib.load()
+    grads = []
+    for disable in (0, 1):
+        prev = L.pwc_set_disable_seq(disable)
+        try:
+            a, b, f, g = to_dev(f1, f2, flow, go)
+            for t in (a, b, f):
+                t.requires_grad_()
+            out = pkg.FusedWarpCorrelation(*CANON_CFG, activation=act)(a, b, f)
+            out.backward(g)
+            torch.cuda.synchronize()
+            grads.append([out.detach(), a.grad.clone(), b.grad.clone(), f.grad.clone()])
+        finally:
+            L.pwc_set_disable_seq(prev)
+    for x, y in zip(*grads):
+        assert max_rel(x.cpu().numpy(), y.cpu().numpy()) < 5e-6
+    if B <= 3:
+        gate = grads[0][0].cpu().numpy()
+        g1, g2, gf = co.warpcorr_backward(go, f1, f2, flow, gate, *CANON_CFG, act=act, slope=0.01)
+        for got, want in zip(grads[0][1:], (g1, g2, gf)):
+            assert max_rel(got.cpu().numpy(), want) < TOL
