@@ -240,7 +240,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -504,7 +504,7 @@ def run_native(args):
             "cpu_baseline": cpu,
             "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -645,6 +645,19 @@ def measure_extras(torch, pkg, dev, sets, make_set):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Writes the one JSON line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -657,9 +670,16 @@ def main():
                          "kernel is then timed alone right before the timed region instead of inside it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "native" and args.gpus > 1 and world == 1):
+        # stdout carries exactly ONE JSON line: every other writer to file descriptor 1 (NCCL's version banner,
+        # library chatter) is sent to stderr at the descriptor level; the line goes to the saved descriptor
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
         import subprocess
