@@ -145,6 +145,10 @@ class Net(nn.Module):
             # l == 0: the flow is identically zero, the warp is the identity (model.py:74-76 still runs it);
             # the kernel is told so and skips taps, window and gather (x2_warp is then x2 itself, bit for bit)
             wflow = None if (l == 0 and self._own_ops) else flow
+            if x1.dtype != torch.float32:      # reduced-precision convolutions (autocast): the hot path is fp32
+                x1, x2 = x1.float(), x2.float()
+                flow = flow.float()
+                wflow = None if wflow is None else flow
             if self._direct_concat and not torch.is_grad_enabled():
                 # inference: the kernel writes the cost volume straight into the estimator's input
                 # [x1 | corr | flow] (model.py:89-91); torch.cat would copy its 81 channels once more
