@@ -14,8 +14,9 @@
 //               tile row lr, column 8*ls.  Per displacement row: 18 LDS.128 (taps) + 4 x (4 LDS.128 +
 //               72 FFMA); at the end of the item 8 STG.128.
 //   T  1 warp : one TMA request per item for the X tile + halo of 32 channels (double buffered).
-//   S  3 warps: stream the taps, one ring slot per (item, displacement row), with cp.async from the
-//               (SIGN < 0: shifted) positions, zero fill outside the image; runs NTS slots ahead.
+//   S  3 warps: stream the taps, one ring slot per (item, displacement row): 16-byte cp.async where the
+//               source is 16-byte aligned (always for SIGN > 0), else aligned LDG.128 pairs + a register
+//               shift + STS.128 (stage_tap_row); zero fill outside the image; runs NTS slots ahead.
 // "Consumed" signals are given only after every instruction that reads the buffer has issued (one
 // loop iteration late, or after dependent stores): an mbarrier arrive can overtake a pending LDS.
 #pragma once
@@ -75,7 +76,7 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < NTS; ++i) {
-            mbar_init(&barTap[i], 32);
+            mbar_init(&barTap[i], 64);          // per staging lane: one cp.async arrival + one plain arrival
             mbar_init(&barTapFree[i], NCONS);
         }
         fence_mbar_init();
@@ -92,39 +93,9 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32) {
                 const int j = it * D + dyi, slot = j % NTS;
                 if (j >= NTS) mbar_wait(&barTapFree[slot], ((j / NTS) - 1) & 1);
-                float* dstb = sTap + slot * Cfg::SLOT_ELEMS;
-                const int dy = (SIGN > 0) ? 0 : (dyi - 4) * S2;
-#pragma unroll
-                for (int dxi = 0; dxi < D; ++dxi) {
-                    const int dx = (SIGN > 0) ? 0 : (dxi - 4) * S2;
-                    const float* plane = gon + (size_t)(dyi * D + dxi) * HW;
-                    if (dx % 4 == 0) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int i = lane + 32 * q, row = i >> 2, x = (i & 3) * 4;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W % 4 == 0: whole quads
-                            cp_async_zfill<16>(dstb + tap_slot(dxi, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 16 : 0);
-                        }
-                    } else if (dx % 2 == 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int i = lane + 32 * q, row = i >> 3, x = (i & 7) * 2;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W is even: whole pairs
-                            cp_async_zfill<8>(dstb + tap_slot(dxi, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 8 : 0);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int i = lane + 32 * q, row = i >> 4, x = i & 15;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;
-                            cp_async_zfill<4>(dstb + tap_slot(dxi, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 4 : 0);
-                        }
-                    }
-                }
-                cp_async_mbar_arrive(&barTap[slot]);       // arrives once this thread's copies have landed
+                stage_tap_row<S2, SIGN>(sTap + slot * Cfg::SLOT_ELEMS, gon, dyi, tc, H, W, HW, lane, gout);
+                cp_async_mbar_arrive(&barTap[slot]);       // arrives once this thread's asynchronous copies have landed
+                mbar_arrive(&barTap[slot]);                // release: this thread's shifted quads are stored
             }
         }
         return;

@@ -10,9 +10,10 @@
 //
 // Persistent CTA (one per SM) walking 16x16 tiles; work item = (tile, chunk of CK channels).
 //   T  1 warp : TMA requests for the X tile + halo chunks (ring of NS).
-//   S  3 warps: stage the NEXT tile's output-gradient taps in shared memory with cp.async (16/8/4-byte
-//               copies from the shifted positions y-dy, x-dx, zero fill outside the image) while the
-//               consumers work on the current tile, so the taps never cost an exposed global round trip.
+//   S  3 warps: stage the NEXT tile's output-gradient taps in shared memory (stage_tap_row: 16-byte
+//               cp.async, or LDG.128 pairs + register shift + STS.128 for the shifted positions y-dy, x-dx,
+//               zero fill outside the image) while the consumers work on the current tile, so the taps
+//               never cost an exposed global round trip.
 //   C  9 warps: warp wd owns displacement row tj = wd - 4; lane (lr, ls) owns an 8-pixel strip and
 //               keeps its 8x9 output-gradient taps in registers for the whole tile (18 conflict-free
 //               LDS.128 from the staging buffer); per channel 4 LDS.128 feed 72 FFMA and
@@ -54,6 +55,63 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ int tap_slot(int d, int row, int x)
 {
     return d * 256 + row * 16 + ((((x >> 2) ^ (row >> 1)) & 3) << 2) + (x & 3);
+}
+
+
+// One displacement row (9 planes, dxi = 0..8) of output-gradient taps for one 16x16 tile -> staging
+// buffer `dst` (9 x 256 floats, tap_slot layout).  plane(dxi)[row][x] = gO[dyi*9+dxi][y0+row-dy][x0+x-dx]
+// (dx = dy = 0 for SIGN > 0), zero outside the image.  Executed by one warp.
+//   * dx % 4 == 0: 16-byte cp.async straight from global memory (zero fill by src-size 0);
+//   * otherwise  : two aligned LDG.128 per output quad, a compile-time register shift, STS.128.
+//     (4-byte cp.async for these planes cost ~6x more LSU cycles and starved the consumers: measured.)
+// All loads of the row are issued before the first store.  The caller signals completion with BOTH
+// cp_async_mbar_arrive() and a normal mbar_arrive() (release for the STS).
+template <int S2, int SIGN>
+__device__ __forceinline__ void stage_tap_row(float* dst, const float* __restrict__ gon, int dyi, const TileCoord& tc,
+                                              int H, int W, size_t HW, int lane, const float* safe)
+{
+    constexpr int D = 9;
+    const int dy = (SIGN > 0) ? 0 : (dyi - 4) * S2;
+    // lane -> two output quads per plane: (row, xq) = (lane >> 2, lane & 3) and (8 + (lane >> 2), lane & 3)
+    const int r0 = lane >> 2, xq = lane & 3;
+    float4 A[D][2], Bq[D][2];
+#pragma unroll
+    for (int dxi = 0; dxi < D; ++dxi) {
+        const int dx = (SIGN > 0) ? 0 : (dxi - 4) * S2;
+        const int sh = ((-dx) % 4 + 4) % 4;
+        const float* plane = gon + (size_t)(dyi * D + dxi) * HW;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int row = r0 + 8 * q;
+            const int sy = tc.y0 + row - dy;
+            const int ab = tc.x0 + 4 * xq - dx - sh;                 // aligned source column of quad A
+            const bool rok = sy >= 0 && sy < H;
+            if (sh == 0) {
+                const bool ok = rok && ab >= 0 && ab < W;            // W % 4 == 0: whole quads
+                cp_async_zfill<16>(dst + tap_slot(dxi, row, 4 * xq), ok ? plane + (size_t)sy * W + ab : safe, ok ? 16 : 0);
+            } else {
+                A[dxi][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                Bq[dxi][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rok && ab >= 0 && ab < W) A[dxi][q] = __ldg(reinterpret_cast<const float4*>(plane + (size_t)sy * W + ab));
+                if (rok && ab + 4 >= 0 && ab + 4 < W) Bq[dxi][q] = __ldg(reinterpret_cast<const float4*>(plane + (size_t)sy * W + ab + 4));
+            }
+        }
+    }
+#pragma unroll
+    for (int dxi = 0; dxi < D; ++dxi) {
+        const int dx = (SIGN > 0) ? 0 : (dxi - 4) * S2;
+        const int sh = ((-dx) % 4 + 4) % 4;
+        if (sh != 0) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 a = A[dxi][q], b = Bq[dxi][q];
+                const float4 o = sh == 1 ? make_float4(a.y, a.z, a.w, b.x)
+                               : sh == 2 ? make_float4(a.z, a.w, b.x, b.y)
+                                         : make_float4(a.w, b.x, b.y, b.z);
+                *reinterpret_cast<float4*>(dst + tap_slot(dxi, r0 + 8 * q, 4 * xq)) = o;
+            }
+        }
+    }
 }
 
 template <int S2_, int CK_>
@@ -119,7 +177,7 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_init(&barPart[i], NCONS);
             mbar_init(&barPartFree[i], NRED);
         }
-        mbar_init(barTap, Cfg::NSTAGE);
+        mbar_init(barTap, 2 * Cfg::NSTAGE);     // per staging thread: one cp.async arrival + one plain arrival
         mbar_init(barTapFree, NCONS);
         fence_mbar_init();
     }
@@ -132,42 +190,10 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
             if (lt >= 1) mbar_wait(barTapFree, (lt - 1) & 1);      // tile lt-1's taps are in the consumers' registers
             const float* gon = gout + (size_t)tc.n * (D * D) * HW;
-            for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32) {
-                const int dy = (SIGN > 0) ? 0 : (dyi - 4) * S2;
-#pragma unroll
-                for (int dxi = 0; dxi < D; ++dxi) {
-                    const int dx = (SIGN > 0) ? 0 : (dxi - 4) * S2;
-                    const int d = dyi * D + dxi;
-                    const float* plane = gon + (size_t)d * HW;
-                    // widest copy the shift allows (tile rows start on multiples of 16 pixels)
-                    if (dx % 4 == 0) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int i = lane + 32 * j, row = i >> 2, x = (i & 3) * 4;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W % 4 == 0: whole quads
-                            cp_async_zfill<16>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 16 : 0);
-                        }
-                    } else if (dx % 2 == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int i = lane + 32 * j, row = i >> 3, x = (i & 7) * 2;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;   // W is even: whole pairs
-                            cp_async_zfill<8>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 8 : 0);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int i = lane + 32 * j, row = i >> 4, x = i & 15;
-                            const int sy = tc.y0 + row - dy, sx = tc.x0 + x - dx;
-                            const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;
-                            cp_async_zfill<4>(sTap + tap_slot(d, row, x), ok ? plane + (size_t)sy * W + sx : gout, ok ? 4 : 0);
-                        }
-                    }
-                }
-            }
-            cp_async_mbar_arrive(barTap);       // arrives once this thread's copies have landed
+            for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32)
+                stage_tap_row<S2, SIGN>(sTap + dyi * D * (TH * TW), gon, dyi, tc, H, W, HW, lane, gout);
+            cp_async_mbar_arrive(barTap);       // arrives once this thread's asynchronous copies have landed
+            mbar_arrive(barTap);                // release: this thread's shifted quads are stored
         }
         return;
     }

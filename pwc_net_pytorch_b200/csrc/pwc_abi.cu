@@ -463,11 +463,10 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
             }
             int r1 = 1, r2 = 1;
             if (g.s2 == 1 && !g_disable_seq.load()) {
-                // g1: threads own complete outputs (90 vs 111 us at the level-2 shape).  The gradient w.r.t. the
-                // second operand stays on the slice/reduce kernel: its taps sit at shifted, 4-byte aligned
-                // positions, and streaming them row by row costs more than the reducer it saves (124 vs 113 us).
+                // threads own complete outputs (corr_bwd_seq.cuh): 90 / 100 us vs 111 / 108 us for the
+                // slice/reduce kernel at the level-2 shape
                 if (which & 1) r1 = launch_bwd_seq<+1>(go, second, g1, g, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_seq<-1>(go, f1, g2, g, st);
             } else if (g.s2 == 1) {
                 if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(go, second, g1, g, st);
                 if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
