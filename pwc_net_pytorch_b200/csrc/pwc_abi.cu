@@ -499,9 +499,10 @@ int warp_backward_v4(const float* grad_out, const float* x, const float* flow, f
         return fail("cudaMemsetAsync(scratch): %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)
         return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
+    if ((long long)H * W > 0x3fffffffLL || B > 65535 || cocts > 65535) return fail("warp backward: tensor too large");
     const size_t total = (size_t)B * H * W * cocts;
-    pwc::warp_bwd_v8_kernel<<<(unsigned)((2 * total + 255) / 256), 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow,
-                                                                                    warped_out, B, C, H, W, cocts);
+    const dim3 grid((unsigned)pwc::cdiv(2 * H * W, 256), (unsigned)cocts, (unsigned)B);
+    pwc::warp_bwd_v8_kernel<<<grid, 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow, warped_out, B, C, H, W, cocts);
     if (!check_launch("warp_bwd_v8_kernel")) return 0;
     pwc::deinterleave8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cocts);
     return check_launch("deinterleave8_kernel");
