@@ -125,12 +125,18 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
 
     // ================================ C: complete outputs ================================
+    // Programmatic dependent launch: once every CTA has started its LAST item (or has none), a kernel that
+    // was launched behind this one with the programmatic-serialization attribute may start on the SMs
+    // that fall idle during the tail (9.08 items per CTA at the level-2 shape: 136 of 148 SMs idle for
+    // the last item).  Such a dependent must not consume this kernel's output (see pwc_abi.cu).
+    if (tid == 0 && my_items <= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = tid & 31, cg = tid >> 5;              // cg: channel group inside the item
     const int lr = lane & 15, ls = lane >> 4;
     const float inv_nelems = __frcp_rn((float)C);          // 1/C, correlation_cuda_kernel.cu:194,286
     int j = 0;                                             // running tap-slot counter
     for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x, xb = it & 1;
+        if (tid == 0 && it == my_items - 1 && my_items > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         const TileCoord tc = tile_coord(item / nsc, tiles_x, tiles_y, TH, TW);
         const int c_base = (item % nsc) * CPI + cg * CK;
         float part[CK][PX];

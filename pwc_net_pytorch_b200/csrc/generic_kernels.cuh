@@ -450,6 +450,20 @@ deinterleave8_kernel(const float* __restrict__ src8, float* __restrict__ dst, in
     }
 }
 
+// Zero fill of two float ranges (na, nb multiples of 4, 16-byte aligned bases) as a KERNEL, so that it can
+// be launched with programmatic dependent launch into the tail of the persistent kernel before it (a
+// cudaMemsetAsync node cannot).  Grid-stride.
+__global__ void __launch_bounds__(256)
+zero2_kernel(float4* __restrict__ a, size_t na4, float4* __restrict__ b, size_t nb4)
+{
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < na4 + nb4; i += stride) {
+        if (i < na4) a[i] = z;
+        else b[i - na4] = z;
+    }
+}
+
 // LeakyReLU backward (model.py:84) as a stand-alone pass: dst = grad_out * (out < 0 ? slope : 1).
 // Feeds the TMA correlation-backward kernels, whose taps are staged by asynchronous copies and cannot
 // be gated on the way.  n4 = number of float4 elements.

@@ -2,6 +2,7 @@
 // Plain pointers and sizes only; no torch types.  Never allocates, frees or synchronises.
 #include "../../include/pwc_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -490,22 +491,76 @@ int corr_backward_impl(const float* gout, const float* gate, const float* f1, co
 
 // Feature-gradient scatter through the 8-channel-interleaved scratch (see warp_bwd_v8_kernel).
 // scratch holds B * ceil(C/8) * H * W * 8 floats, 16-byte aligned.
+// Launch `kern` so that it may start while the kernel before it in the stream is still running its tail
+// (programmatic dependent launch).  Only for kernels that do NOT read what that kernel writes.
+template <class Kern, class... Args>
+cudaError_t launch_into_tail(Kern kern, dim3 grid, dim3 block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+// Zeroes the scatter scratch (B * ceil(C/8) * H * W * 8 floats) and the flow gradient.  Launched right
+// behind the kernel that computes the gradient w.r.t. the warped features, into its tail.
+int scatter_zero(float* scratch, float* grad_flow, int B, int C, int H, int W, cudaStream_t stream)
+{
+    const size_t n8 = (size_t)B * pwc::cdiv(C, 8) * H * W * 8, nf = (size_t)B * 2 * H * W;
+    if ((nf & 3) == 0 && (((uintptr_t)scratch | (uintptr_t)grad_flow) & 15) == 0) {
+        const unsigned grid = (unsigned)std::min<size_t>((n8 / 4 + nf / 4 + 255) / 256, (size_t)148 * 8);
+        if (launch_into_tail(pwc::zero2_kernel, dim3(grid), dim3(256), stream, reinterpret_cast<float4*>(scratch), n8 / 4,
+                             reinterpret_cast<float4*>(grad_flow), nf / 4) != cudaSuccess)
+            return fail("zero2_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+        return check_launch("zero2_kernel");
+    }
+    if (cudaMemsetAsync(scratch, 0, sizeof(float) * n8, stream) != cudaSuccess ||
+        cudaMemsetAsync(grad_flow, 0, sizeof(float) * nf, stream) != cudaSuccess)
+        return fail("cudaMemsetAsync(scatter scratch): %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+}
+
+// Feature-gradient scatter through the 8-channel-interleaved scratch (see warp_bwd_v8_kernel); the scratch
+// and grad_flow must have been zeroed (scatter_zero).  scratch is 16-byte aligned.
+int scatter_accumulate(const float* grad_out, const float* x, const float* flow, float* grad_flow, float* scratch,
+                       float* warped_out, int B, int C, int H, int W, cudaStream_t stream)
+{
+    const int cocts = pwc::cdiv(C, 8);
+    if ((long long)H * W > 0x3fffffffLL || B > 65535 || cocts > 65535) return fail("warp backward: tensor too large");
+    const dim3 grid((unsigned)pwc::cdiv(2 * H * W, 256), (unsigned)cocts, (unsigned)B);
+    pwc::warp_bwd_v8_kernel<<<grid, 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow, warped_out, B, C, H, W, cocts);
+    return check_launch("warp_bwd_v8_kernel");
+}
+
+// scratch -> NCHW grad_x.  `into_tail`: the kernel before it in the stream does not write the scratch, so
+// the de-interleave may start in that kernel's tail.
+int scatter_finish(const float* scratch, float* grad_x, int B, int C, int H, int W, bool into_tail, cudaStream_t stream)
+{
+    const int cocts = pwc::cdiv(C, 8);
+    const size_t total = (size_t)B * H * W * cocts;
+    const dim3 grid((unsigned)((total + 255) / 256));
+    if (into_tail) {
+        if (launch_into_tail(pwc::deinterleave8_kernel, grid, dim3(256), stream, scratch, grad_x, B, C, H, W, cocts) != cudaSuccess)
+            return fail("deinterleave8_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        pwc::deinterleave8_kernel<<<grid, 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cocts);
+    }
+    return check_launch("deinterleave8_kernel");
+}
+
 int warp_backward_v4(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
                      float* scratch, float* warped_out, int B, int C, int H, int W, cudaStream_t stream)
 {
-    const int cocts = pwc::cdiv(C, 8);
-    const size_t n8 = (size_t)B * cocts * H * W * 8;
-    if (cudaMemsetAsync(scratch, 0, sizeof(float) * n8, stream) != cudaSuccess)
-        return fail("cudaMemsetAsync(scratch): %s", cudaGetErrorString(cudaGetLastError()));
-    if (cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)
-        return fail("cudaMemsetAsync(grad_flow): %s", cudaGetErrorString(cudaGetLastError()));
-    if ((long long)H * W > 0x3fffffffLL || B > 65535 || cocts > 65535) return fail("warp backward: tensor too large");
-    const size_t total = (size_t)B * H * W * cocts;
-    const dim3 grid((unsigned)pwc::cdiv(2 * H * W, 256), (unsigned)cocts, (unsigned)B);
-    pwc::warp_bwd_v8_kernel<<<grid, 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow, warped_out, B, C, H, W, cocts);
-    if (!check_launch("warp_bwd_v8_kernel")) return 0;
-    pwc::deinterleave8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scratch, grad_x, B, C, H, W, cocts);
-    return check_launch("deinterleave8_kernel");
+    return scatter_zero(scratch, grad_flow, B, C, H, W, stream) &&
+           scatter_accumulate(grad_out, x, flow, grad_flow, scratch, warped_out, B, C, H, W, stream) &&
+           scatter_finish(scratch, grad_x, B, C, H, W, false, stream);
 }
 
 }  // namespace
@@ -625,12 +680,17 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     if (vec_ok && split_ok) {
         // 1. gradient w.r.t. the warped features (needs f1 and grad_out only)
         if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2, gated, &gated_done)) return 0;
-        // 2. scatter to grad_f2 + flow gradient; the same pass re-materialises x2_warp when the forward did
+        // 2. zero the scatter scratch: independent of step 1, launched into its tail
+        if (!scatter_zero(scratch, grad_flow, B, C, H, W, stream)) return 0;
+        // 3. scatter to the scratch + flow gradient; the same pass re-materialises x2_warp when the forward did
         //    not export it (both need the four bilinear corner values)
-        if (!warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, warped_in ? nullptr : wbuf, B, C, H, W, stream))
+        if (!scatter_accumulate(gwarped, f2, flow, grad_flow, scratch, warped_in ? nullptr : wbuf, B, C, H, W, stream))
             return 0;
-        // 3. gradient w.r.t. f1 (needs x2_warp)
-        return corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1, gated, &gated_done);
+        // 4. gradient w.r.t. f1 (needs x2_warp, does not touch the scratch)
+        if (!corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1, gated, &gated_done))
+            return 0;
+        // 5. scratch -> grad_f2 (NCHW): independent of step 4, launched into its tail
+        return scatter_finish(scratch, grad_f2, B, C, H, W, true, stream);
     }
     const float* warped = warped_in;
     if (!warped) {      // re-materialise x2_warp (the forward never stored it)
