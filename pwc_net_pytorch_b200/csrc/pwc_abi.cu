@@ -14,6 +14,7 @@
 #include "generic_kernels.cuh"
 #include "pwc_common.cuh"
 #include "small_image.cuh"
+#include "warp_bwd_tile.cuh"
 #include "warpcorr_fwd.cuh"
 #include "warpcorr_fwd_tma.cuh"
 
@@ -534,6 +535,32 @@ int scatter_accumulate(const float* grad_out, const float* x, const float* flow,
 {
     const int cocts = pwc::cdiv(C, 8);
     if ((long long)H * W > 0x3fffffffLL || B > 65535 || cocts > 65535) return fail("warp backward: tensor too large");
+    // tiled kernel (corner values from a TMA-staged shared-memory window) where TMA applies
+    if (!g_disable_tma.load() && (W & 3) == 0 && W >= 16 && H >= 8 && W < 32760 && H < 32760 &&
+        (((uintptr_t)x | (uintptr_t)scratch) & 15) == 0) {
+        using Cfg = pwc::WarpBwdCfg;
+        CUtensorMap mX;
+        if (make_nchw_map(&mX, x, B, C, H, W, Cfg::WW, Cfg::WH, Cfg::CK)) {
+            auto kern = pwc::warp_bwd_tile_kernel;
+            const size_t smem = Cfg::smem_bytes();
+            static thread_local int configured_dev = -1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (configured_dev != dev) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                    return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
+                configured_dev = dev;
+            }
+            const int tiles_x = pwc::cdiv(W, Cfg::TW), tiles_y = pwc::cdiv(H, Cfg::TH);
+            const long long ntiles = (long long)tiles_x * tiles_y * B;
+            if (ntiles > 0x3fffffffLL) return fail("grid too large");
+            const long long cap = 3LL * sm_count_of_current_device();
+            const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+            kern<<<grid, Cfg::NT, smem, stream>>>(mX, grad_out, x, flow, scratch, grad_flow, warped_out, C, H, W, tiles_x,
+                                                 tiles_y, (int)ntiles, cocts);
+            return check_launch("warp_bwd_tile_kernel");
+        }
+    }
     const dim3 grid((unsigned)pwc::cdiv(2 * H * W, 256), (unsigned)cocts, (unsigned)B);
     pwc::warp_bwd_v8_kernel<<<grid, 256, 0, stream>>>(grad_out, x, flow, scratch, grad_flow, warped_out, B, C, H, W, cocts);
     return check_launch("warp_bwd_v8_kernel");
