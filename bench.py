@@ -546,10 +546,14 @@ def run_native(args):
 
 
 def time_cuda(torch, fn, iters=20, warm=3):
+    """Mean device time of fn() over `iters` back-to-back calls.  A device-side sleep is queued first so
+    that the launches are already enqueued when the GPU reaches them: short kernels (coarse pyramid
+    levels, 10-20 us) are then not measured at the pace of the Python launch path."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(2.0e6 * max(1, iters // 10)))      # ~1 ms per 10 queued calls
     e0.record()
     for _ in range(iters):
         fn()
