@@ -1,3 +1,5 @@
+"""GPU-vs-GPU check at the full level-2 size: backward through the TMA / seq kernels against the plain tiled
+kernels (pwc_set_disable_tma), printing the positions of any mismatch.  usage: python scripts/check_backward_fullsize.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -1,3 +1,5 @@
+"""Oracle check of shapes that give every persistent CTA several tiles (ring / release-order bugs show up
+only there).  usage: python scripts/check_backward_multitile.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
