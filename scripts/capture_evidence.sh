@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --eager --steps 3 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2>&1
 # full captures, one launch per kernel
 python scripts/prof_case.py fwdbwd level2 iid canon 2 > /dev/null 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:"warpcorr_fwd_tma|corr_bwd_seq|warp_bwd_v8|deinterleave8" -c 5 \
+ncu --set full --import-source on --clock-control none -k regex:"warpcorr_fwd_tma|corr_bwd_seq|warp_bwd_tile|zero2|deinterleave8" -c 6 \
     -o $O/${R}_level2_fwdbwd python scripts/prof_case.py fwdbwd level2 iid canon 1 > /dev/null 2>&1
 python scripts/prof_case.py fwdbwd level6 iid canon 2 > /dev/null 2>&1 && \
 ncu --set full --import-source on --clock-control none -k regex:"small_kernel" -c 2 \
