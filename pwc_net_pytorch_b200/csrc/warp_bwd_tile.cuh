@@ -46,7 +46,7 @@ warp_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF2, const float* __re
     using Cfg = WarpBwdCfg;
     constexpr int CK = Cfg::CK, TW = Cfg::TW, TH = Cfg::TH, WW = Cfg::WW, WH = Cfg::WH, NWIN = Cfg::NWIN, NB = Cfg::NB;
 
-    extern __shared__ __align__(128) uint8_t base[];
+    extern __shared__ __align__(1024) uint8_t base[];
     uint64_t* barWin = reinterpret_cast<uint64_t*>(base);     // [NWIN] TMA: window chunk landed      (T -> B)
     uint64_t* barWinFree = barWin + NWIN;                     // [NWIN] window chunk consumed          (B -> T)
     uint64_t* barOrg = barWinFree + NWIN;                     // [2]    window origin of a tile known  (B -> T)
