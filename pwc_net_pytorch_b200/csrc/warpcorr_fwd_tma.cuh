@@ -415,6 +415,11 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
             const float* win = sWin + (g % NWIN) * Cfg::WIN_ELEMS;
             float* w2buf = sW2 + s * Cfg::W2_ELEMS;
             float v[PXB][CK];
+            // The corner loads go out in groups of 8 (two channels of one pixel; the empty asm is a compiler-
+            // level fence that keeps the groups apart).  64 loads per thread in one burst kept the LSU queue
+            // full of this role's conflicting scalar loads, and the consumers' LDS.128 waited behind them:
+            // bursts of 64 / 16 / 8 / 4 loads -> 118.5 / 117.3 / 112.8 / 118.2 us at the level-2 shape.  The
+            // stores stay together at the end (storing each pixel at once: 128 us).
 #pragma unroll
             for (int j = 0; j < PXB; ++j) {
                 const float* p = win + (toff[j] >= 0 ? toff[j] : 0);     // empty / none / global: a safe address
@@ -422,6 +427,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                 for (int c = 0; c < CK; ++c) {
                     const float* q = p + c * (WH * WW);
                     v[j][c] = fmaf(tw[j].w, q[WW + 1], fmaf(tw[j].z, q[WW], fmaf(tw[j].y, q[1], tw[j].x * q[0])));
+                    if (c & 1) asm volatile("" ::: "memory");
                 }
             }
             if (any_global) {
