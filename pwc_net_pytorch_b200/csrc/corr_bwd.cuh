@@ -34,7 +34,7 @@ corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
                 int C, int H, int W, int tiles_x, int tiles_y, int cgroup, float slope)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, r = Cfg::r, R = Cfg::R;
-    constexpr int TW = Cfg::TW, TH = Cfg::TH, NT = Cfg::NT, HH = Cfg::HH, HWD = Cfg::HWD, HP = Cfg::HP;
+    constexpr int TW = Cfg::TW, TH = Cfg::TH, NT = Cfg::NT, HH = Cfg::HH, HP = Cfg::HP;
     extern __shared__ __align__(16) float sX[];
 
     const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;

@@ -237,112 +237,13 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
 // Feature-gradient scatter with 128-bit reductions.  The scalar scatter above is bound by the SM's
 // reduction-issue rate (one RED.E.ADD.F32 per lane, corner and channel: 1.29 cycles each, measured).
 // Here four channels share one REDG.E.ADD.F32x4 (red.global.add.v4.f32, sm_90+): the gradient is
-// accumulated in a scratch buffer laid out [B][ceil(C/4)][H][W][4] (zeroed by the caller), and
-// deinterleave4_kernel then writes the NCHW result (which therefore needs no memset).
-// One thread per (n, channel quad, y, x).
-__global__ void __launch_bounds__(256)
-warp_bwd_v4_kernel(const float* __restrict__ gout, const float* __restrict__ x,
-                   const float* __restrict__ flow, float* __restrict__ gx4,
-                   float* __restrict__ gflow, float* __restrict__ warped_out, int B, int C, int H, int W, int cquads)
-{
-    // warped_out != nullptr: the kernel also writes the warped features (the same four corner values
-    // feed the flow gradient), which lets the fused backward skip a separate warp_fwd_kernel pass.
-    const size_t HW = (size_t)H * W;
-    const size_t total = (size_t)B * HW * cquads;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t pix = idx % HW;
-    const int cq = (int)((idx / HW) % cquads);
-    const int n = (int)(idx / (HW * cquads));
-    const int yy = pix / W, xx = pix - yy * W;
-    const float u = __ldg(flow + (size_t)n * 2 * HW + pix);
-    const float v = __ldg(flow + (size_t)n * 2 * HW + HW + pix);
-    float ax = 0.0f, ay = 0.0f;
-    int x0 = 0, y0 = 0;
-    const Tap t = make_tap(xx, yy, u, v, H, W, &ax, &ay, &x0, &y0);
-    if (t.off < 0) {                // nothing to scatter, zero flow gradient (the buffers are zeroed)
-        if (warped_out) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (4 * cq + k < C) warped_out[((size_t)n * C + 4 * cq + k) * HW + pix] = 0.0f;
-        }
-        return;
-    }
-    const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
-    const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
-    const float m10 = (inx0 && iny1) ? 1.0f : 0.0f, m11 = (inx1 && iny1) ? 1.0f : 0.0f;
-    float g[4];
-    float gu = 0.0f, gv = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = 4 * cq + k;
-        g[k] = 0.0f;
-        if (c < C) {
-            const size_t plane = ((size_t)n * C + c) * HW;
-            g[k] = __ldg(gout + plane + pix);
-            const float* p = x + plane + t.off;
-            const float v00 = m00 * __ldg(p), v01 = m01 * __ldg(p + t.dx);
-            const float v10 = m10 * __ldg(p + t.dyw), v11 = m11 * __ldg(p + t.dyw + t.dx);
-            gu = fmaf(g[k], fmaf(v11 - v10, ay, (v01 - v00) * (1.0f - ay)), gu);
-            gv = fmaf(g[k], fmaf(v11 - v01, ax, (v10 - v00) * (1.0f - ax)), gv);
-            if (warped_out)   // same expression as tap_sample (weights of masked corners are 0)
-                warped_out[plane + pix] = fmaf(t.w11, v11, fmaf(t.w10, v10, fmaf(t.w01, v01, t.w00 * v00)));
-        }
-    }
-    if (gx4) {
-        float* q = gx4 + (((size_t)n * cquads + cq) * HW + t.off) * 4;
-        const size_t sdx = (size_t)t.dx * 4, sdy = (size_t)t.dyw * 4;
-        if (t.w00 != 0.0f)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(g[0] * t.w00), "f"(g[1] * t.w00),
-                         "f"(g[2] * t.w00), "f"(g[3] * t.w00) : "memory");
-        if (t.w01 != 0.0f)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdx), "f"(g[0] * t.w01), "f"(g[1] * t.w01),
-                         "f"(g[2] * t.w01), "f"(g[3] * t.w01) : "memory");
-        if (t.w10 != 0.0f)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdy), "f"(g[0] * t.w10), "f"(g[1] * t.w10),
-                         "f"(g[2] * t.w10), "f"(g[3] * t.w10) : "memory");
-        if (t.w11 != 0.0f)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + sdy + sdx), "f"(g[0] * t.w11),
-                         "f"(g[1] * t.w11), "f"(g[2] * t.w11), "f"(g[3] * t.w11) : "memory");
-    }
-    if (gflow) {
-        float* gf = gflow + (size_t)n * 2 * HW + pix;
-        if (cquads == 1) {
-            gf[0] = gu;
-            gf[HW] = gv;
-        } else {
-            atomicAdd(gf, gu);
-            atomicAdd(gf + HW, gv);
-        }
-    }
-}
-
-// [B][ceil(C/4)][H][W][4] scratch -> NCHW gradient (fully overwrites the destination).
-__global__ void __launch_bounds__(256)
-deinterleave4_kernel(const float* __restrict__ src4, float* __restrict__ dst, int B, int C, int H, int W, int cquads)
-{
-    const size_t HW = (size_t)H * W;
-    const size_t total = (size_t)B * HW * cquads;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t pix = idx % HW;
-    const int cq = (int)((idx / HW) % cquads);
-    const int n = (int)(idx / (HW * cquads));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src4) + ((size_t)n * cquads + cq) * HW + pix);
-    const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = 4 * cq + k;
-        if (c < C) dst[((size_t)n * C + c) * HW + pix] = vals[k];
-    }
-}
-
-// Same scatter with an 8-channel interleave: scratch [B][ceil(C/8)][H][W][8] (zeroed by the caller).
-// Two adjacent lanes own the two channel quads of one (pixel, channel octet), so their two
-// red.global.add.v4.f32 fall into the SAME 32-byte sector: the LSU issues one sector request per lane
-// pair instead of one per lane (the scatter is bound by those requests: 64% of its L1 wavefronts were
-// reduction sectors with the 4-channel layout).  The pair also sums its flow-gradient terms with one
-// shuffle before the atomic.  One thread per (n, channel octet, y, x, half).
+// accumulated in a scratch buffer laid out [B][ceil(C/8)][H][W][8] (zeroed by the caller), and
+// deinterleave8_kernel then writes the NCHW result (which therefore needs no memset).
+// Two adjacent lanes own the two channel quads of one (pixel, channel octet), so their two reductions
+// fall into the SAME 32-byte sector: one sector request per lane pair instead of one per lane (5.7 M
+// instead of 10.9 M reduction sectors at the level-2 shape).  The pair also sums its flow-gradient
+// terms with one shuffle before the atomic.  One thread per (n, channel octet, y, x, half).
+// (Fallback of warp_bwd_tile.cuh for W % 4 != 0 or unaligned pointers.)
 __global__ void __launch_bounds__(256)
 warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                    const float* __restrict__ flow, float* __restrict__ gx8,

@@ -582,7 +582,7 @@ int scatter_finish(const float* scratch, float* grad_x, int B, int C, int H, int
     return check_launch("deinterleave8_kernel");
 }
 
-int warp_backward_v4(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
+int warp_backward_scratch(const float* grad_out, const float* x, const float* flow, float* grad_x, float* grad_flow,
                      float* scratch, float* warped_out, int B, int C, int H, int W, cudaStream_t stream)
 {
     return scatter_zero(scratch, grad_flow, B, C, H, W, stream) &&
@@ -725,7 +725,7 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
         warped = wbuf;
     }
     if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream, 3, gated, &gated_done)) return 0;
-    if (vec_ok) return warp_backward_v4(gwarped, f2, flow, grad_f2, grad_flow, scratch, nullptr, B, C, H, W, stream);
+    if (vec_ok) return warp_backward_scratch(gwarped, f2, flow, grad_f2, grad_flow, scratch, nullptr, B, C, H, W, stream);
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
 }
 
