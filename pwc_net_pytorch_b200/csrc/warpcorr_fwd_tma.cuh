@@ -129,6 +129,10 @@ struct TmaCfg {
     static_assert(WIN_BYTES % 128 == 0 && F1_BYTES % 128 == 0 && W2_BYTES % 128 == 0 && FLOW_BYTES % 128 == 0,
                   "buffers stay 128B aligned");
     static_assert(NBARS * 8 + 16 <= CTRL_BYTES, "control block too small");
+    // Deadlock freedom of the T warp: in iteration g it waits for f1 slot (g + NS) % NF1, i.e. for item
+    // g + NS - NF1, which the consumers release one chunk late (after chunk g + NS - NF1 + 1); the window of
+    // that chunk must already have been requested (iteration g - 1 requested windows below g - 1 + NWIN).
+    static_assert(NF1 > NS + 2 - NWIN && NS >= 2, "ring depths would deadlock the TMA warp (measured: a hang)");
 
     static constexpr size_t smem_bytes(bool has_flow)
     {
