@@ -93,3 +93,30 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
                 assert "pwc_oracle" not in txt, os.path.join(dp, f)
+
+
+def test_header_compiles_as_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: include/pwc_b200.h must be valid C (no CUDA headers needed), and a plain C
+    program must link against libpwc_b200.so and call it (version + output-shape arithmetic run without a GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "pwc_b200.h"\n'
+        "int main(void) {\n"
+        "    int oc = 0, oh = 0, ow = 0;\n"
+        "    if (pwc_abi_version() != PWC_B200_ABI_VERSION) return 2;\n"
+        "    if (!pwc_corr_output_shape(96, 112, 4, 1, 4, 1, 1, &oc, &oh, &ow)) return 3;\n"
+        "    if (oc != 81 || oh != 96 || ow != 112) return 4;\n"
+        "    if (pwc_corr_output_shape(96, 112, 4, 2, 4, 1, 1, &oc, &oh, &ow)) return 5;   /* even kernel_size is refused */\n"
+        '    printf("%s\\n", pwc_last_error());\n'
+        "    return 0;\n}\n")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lpwc_b200", "-Wl,-rpath," + libdir])
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    assert "kernel_size" in p.stdout
