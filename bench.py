@@ -152,16 +152,62 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's PyTorch-level path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_path_step(inputs, backward=True):
-    """WarpingLayer -> CostVolumeLayer (modules.py:31-42, :52-74) fwd (+ autograd bwd) on CPU."""
-    from oracle import torch_ref as tr
+_REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_modules():
+    """The reference's own, unmodified modules.py / utils.py (WarpingLayer, CostVolumeLayer), installed
+    into the git-ignored baseline/_ref/ by __graft_entry__.build() when /root/reference is present (the
+    reference has no setup.py, so `pip install --target baseline/_ref` does not apply; the two files are
+    copied as they are).  Returns (warp, cost_volume) callables or None.  The only intervention is the one
+    the parity pins use as well: grid_sample is called with align_corners=True, the torch-0.4.0 behaviour
+    the reference was written against."""
+    if not (os.path.exists(os.path.join(_REF_DIR, "modules.py")) and os.path.exists(os.path.join(_REF_DIR, "utils.py"))):
+        return None
+    try:
+        import importlib.util
+        import types
+
+        import torch
+        import torch.nn.functional as F
+        mods = {}
+        for name in ("utils", "modules"):       # loaded under private names: nothing else sees them
+            spec = importlib.util.spec_from_file_location(f"_pwc_reference_{name}", os.path.join(_REF_DIR, f"{name}.py"))
+            m = importlib.util.module_from_spec(spec)
+            if name == "modules":
+                sys.modules["utils"] = mods["utils"]        # modules.py:8 `from utils import get_grid`
+            try:
+                spec.loader.exec_module(m)
+            finally:
+                if name == "modules":
+                    sys.modules.pop("utils", None)
+            mods[name] = m
+        ref = mods["modules"]
+        fns = types.SimpleNamespace(**{k: getattr(F, k) for k in dir(F) if not k.startswith("__")})
+        fns.grid_sample = lambda x, grid: F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros",
+                                                        align_corners=True)
+        ref.F = fns
+        a = types.SimpleNamespace(device=torch.device("cpu"), search_range=4)
+        return ref.WarpingLayer(a), ref.CostVolumeLayer(a)
+    except Exception:
+        return None
+
+
+def cpu_path_step(inputs, backward=True, ref=None):
+    """WarpingLayer -> CostVolumeLayer (modules.py:31-42, :52-74) fwd (+ autograd bwd) on CPU: the
+    reference's own modules when available (`ref`), else their port in oracle/torch_ref.py."""
+    if ref is None:
+        from oracle import torch_ref as tr
+        warp, cost = tr.warping_layer_port, (lambda a, b: tr.cost_volume_layer_port(a, b, 4))
+    else:
+        warp, cost = ref
     pairs = 0
     for (f1, f2, flow, gout) in inputs:
         if backward:
             f1 = f1.detach().requires_grad_()
             f2 = f2.detach().requires_grad_()
             flow = flow.detach().requires_grad_()
-        out = tr.cost_volume_layer_port(f1, tr.warping_layer_port(f2, flow), 4)
+        out = cost(f1, warp(f2, flow))
         if backward:
             out.backward(gout)
         pairs = max(pairs, f1.shape[0])
@@ -186,17 +232,20 @@ def time_cpu_path(steps, warmup, sample_pairs):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inputs = make_cpu_inputs(torch, sample_pairs)
+    ref = reference_modules()
     for _ in range(warmup):
-        cpu_path_step(inputs)
+        cpu_path_step(inputs, ref=ref)
     t0 = time.perf_counter()
     for _ in range(steps):
-        pairs = cpu_path_step(inputs)
+        pairs = cpu_path_step(inputs, ref=ref)
     dt = time.perf_counter() - t0
+    what = ("the reference's own modules.WarpingLayer + CostVolumeLayer (unmodified files in baseline/_ref, "
+            "grid_sample at align_corners=True)" if ref is not None else
+            "oracle/torch_ref.py port of modules.WarpingLayer+CostVolumeLayer")
     return {
-        "value": pairs * steps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+        "value": pairs * steps / dt, "unit": "pairs/s", "cores": cores, "kind": "reference" if ref is not None else "port",
         "sample": (f"{sample_pairs} of {PAIRS_PER_GPU} pairs per step, both shapes, fwd+bwd (autograd), "
-                   f"{steps} steps after {warmup} warm-up; oracle/torch_ref.py port of "
-                   "modules.WarpingLayer+CostVolumeLayer, torch CPU"),
+                   f"{steps} steps after {warmup} warm-up; {what}, torch CPU"),
         "ms_per_step": 1e3 * dt / steps,
     }
 
@@ -226,8 +275,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 3))
+    # same step / warm-up counts as the native arm; each step is a bounded sample (8 of the 32 pairs,
+    # ~0.2 s of host work), the step count is capped so that the run ends within a few minutes
+    steps = max(1, min(args.steps, 200))
+    warmup = max(0, min(args.warmup, 10))
     res = time_cpu_path(steps, warmup, CPU_SAMPLE_PAIRS)
     cfg = base_config()
     cfg["cpu"] = cpu_model_name()
@@ -495,10 +546,17 @@ def run_native(args):
     barrier()
     e2e_value, _ = parallel.job_throughput(PAIRS_PER_GPU * e2e_steps, e_start.elapsed_time(e_end), dev)
 
-    # ---- per-kernel breakdown + extras (rank 0, outside the timed region) ----
+    # ---- whole-network legs (all ranks) + per-kernel breakdown (rank 0), outside the timed region ----
     extras = {}
+    legs = {}
+    if not args.no_extras:
+        dev_in.clear()       # release the e2e buffers before the network legs
+        host.clear()
+        torch.cuda.empty_cache()
+        legs = measure_network_legs(torch, dist, dev, rank, world, args.dump_kernels)
     if rank == 0 and not args.no_extras:
         extras = measure_extras(torch, pkg, dev, sets, make_set)
+        extras.update(legs)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -543,6 +601,177 @@ def run_native(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-network legs (ALL ranks): BASELINE.json configs 3, 4 and 5 around the hot path
+# ------------------------------------------------------------------------------------------------
+FULL_PYRAMID_LEGS = [   # name, pairs per GPU, H, W, replayed from a CUDA graph
+    ("448x384_B1", 1, 384, 448, True),        # config 1 shape on the GPU: batch-1 latency
+    ("448x384_B64", 64, 384, 448, False),     # the north star's "pairs/s @448x384"
+    ("384x512_B64", 64, 384, 512, False),     # config 3: FlyingChairs-shaped, batch 64 per GPU
+    ("1024x448_B1", 1, 448, 1024, True),      # config 5: Sintel-shaped latency / throughput
+    ("1024x448_B16", 16, 448, 1024, False),
+    ("1280x384_B1", 1, 384, 1280, True),      # config 5: KITTI 1242x375 padded to 1280x384
+    ("1280x384_B16", 16, 384, 1280, False),
+]
+
+
+def measure_network_legs(torch, dist, dev, rank, world, dump_kernels=None):
+    """Config 4 (DDP training step, the project's only collective) and configs 3/5 (full-pyramid
+    inference) with the fused operator in the loop.  Every rank runs them on its own image pairs; a
+    figure is all ranks' pairs divided by the slowest rank's device time.  Each leg carries a same-run
+    parity assertion against the torch oracle operators (the checker, never the thing timed)."""
+    from pwc_net_pytorch_b200 import parallel
+    from pwc_net_pytorch_b200.workloads import PyramidInference, TrainStep, multiscale_l1
+    from pwc_net_pytorch_b200.model import Net, default_args
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) / iters, dev)
+
+    tf32 = bool(torch.backends.cudnn.allow_tf32)
+
+    # ---- parity of the training path at a small shape: fused operator vs torch oracle operators ----
+    parity = {}
+    try:
+        from oracle.model_ops import TorchCorrelationOps, deterministic_init
+        torch.backends.cudnn.allow_tf32 = False
+        a = default_args(device=dev)
+        nets = (Net(a).train(), Net(a, ops=TorchCorrelationOps(4)).train())
+        g = torch.Generator().manual_seed(5)
+        x = (torch.rand(2, 3, 2, 128, 192, generator=g) * 255.0).to(dev)
+        gt = (torch.randn(2, 2, 128, 192, generator=g) * 3.0).to(dev)
+        losses, grads = [], []
+        for net in nets:
+            deterministic_init(net, seed=4)
+            flows, _ = net(x)
+            loss = multiscale_l1(flows, gt)
+            net.zero_grad()
+            loss.backward()
+            losses.append(float(loss.detach()))
+            grads.append({k: p.grad for k, p in net.named_parameters() if p.grad is not None})
+        gerr = max(float((grads[0][k] - grads[1][k]).abs().max() / grads[1][k].abs().max().clamp_min(1e-30))
+                   for k in grads[1])
+        parity = {"loss_rel_diff": abs(losses[0] - losses[1]) / abs(losses[1]), "param_grad_max_rel_diff": gerr,
+                  "shape": "2 pairs 128x192, fp32 convs, fused CUDA op vs torch oracle ops in the same network"}
+        parity["ok"] = bool(parity["loss_rel_diff"] <= 1e-6 and gerr <= 1e-2)
+        del nets, grads
+    except Exception as e:
+        parity = {"error": repr(e)}
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+
+    # ---- config 4: training step, batch 8 per GPU, 384x448 ----
+    train = {"workload": "PWC-Net training step: fwd + MultiScale L1 (losses.py:80-98) + bwd through the fused "
+                         "warp/corr op + Adam(lr 1e-4, wd 4e-4); 8 pairs/GPU 384x448; DDP gradient all-reduce "
+                         "over NCCL for N > 1",
+             "tf32_convs": tf32, "hot_path_dtype": "f32", "parity_small_shape": parity}
+    try:
+        for unused in ("find", "freeze"):
+            ts = TrainStep(dev, batch=8, height=384, width=448, unused=unused)
+            first = float(ts.step())
+            ms = timed(ts.step, iters=6, warm=2)
+            row = {"ms_per_step": ms, "pairs_per_s": world * ts.batch / (ms * 1e-3),
+                   "allreduce_bytes": ts.grad_bytes(), "bucket_cap_mb": ts.bucket_cap_mb,
+                   "loss_first": first, "loss_last": float(ts.step())}
+            if world > 1:
+                ms_local = timed(lambda: ts.step(sync=False), iters=6, warm=1)
+                flat = torch.empty(ts.grad_bytes() // 4, device=dev)
+                ms_ar = timed(lambda: dist.all_reduce(flat), iters=10, warm=3)
+                row.update({"ms_per_step_without_allreduce": ms_local, "allreduce_exposed_ms": ms - ms_local,
+                            "allreduce_alone_ms": ms_ar,
+                            "allreduce_alone_GBps_busbw": ts.grad_bytes() * 2 * (world - 1) / world / ms_ar / 1e6})
+                if unused == "find":
+                    row["nccl_kernels"] = profile_nccl(torch, ts, rank, dump_kernels)
+            train["find_unused_parameters" if unused == "find" else "lv5_lv6_frozen"] = row
+            del ts
+            torch.cuda.empty_cache()
+        train["pairs_per_s"] = train["find_unused_parameters"]["pairs_per_s"]
+    except Exception as e:
+        train["error"] = repr(e)
+    out["train_step_ddp"] = train
+
+    # ---- configs 3 and 5 (+ the 448x384 figures): full-pyramid inference ----
+    torch.manual_seed(0)
+    net = Net(default_args(device=dev)).eval()
+    for name, B, H, W, graphed in FULL_PYRAMID_LEGS:
+        try:
+            leg = PyramidInference(dev, B, H, W, graphed=graphed, net=net)
+            ms = timed(leg.run, iters=5 if B > 1 else 20, warm=2)
+            out[f"full_pyramid_{name}"] = {"ms": ms, "pairs_per_s": world * B / (ms * 1e-3), "pairs_per_gpu": B,
+                                           "launch": "cuda_graph" if graphed else "eager", "tf32_convs": tf32}
+            del leg
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[f"full_pyramid_{name}"] = {"error": repr(e)}
+    # same-run parity: end-point-error delta of the full forward, fused CUDA op vs torch oracle ops, fp32 convs
+    try:
+        from oracle.model_ops import TorchCorrelationOps
+        torch.backends.cudnn.allow_tf32 = False
+        oracle_net = Net(default_args(device=dev), ops=TorchCorrelationOps(4)).eval()
+        oracle_net.load_state_dict(net.state_dict())
+        for name, H, W in (("384x512", 384, 512), ("1024x448", 448, 1024), ("1280x384", 384, 1280)):
+            g = torch.Generator().manual_seed(H + W)
+            x = (torch.rand(1, 3, 2, H, W, generator=g) * 255.0).to(dev)
+            with torch.no_grad():
+                fa, _ = net(x)
+                fb, _ = oracle_net(x)
+            epe = max(float(torch.norm(a - b, p=2, dim=1).max()) for a, b in zip(fa, fb))
+            out[f"full_pyramid_epe_delta_px_{name}"] = {"max_epe_delta_px": epe, "ok": bool(epe <= 1e-4),
+                                                        "bound": 1e-4}
+        del oracle_net
+    except Exception as e:
+        out["full_pyramid_epe_error"] = repr(e)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    del net
+    torch.cuda.empty_cache()
+    return out
+
+
+def profile_nccl(torch, ts, rank, dump_path=None):
+    """Device time of the NCCL kernels inside the DDP step, from the CUPTI kernel trace of three steps
+    (torch.profiler).  Returns None when the trace is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        ts.step()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                ts.step()
+            torch.cuda.synchronize()
+        rows = {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is not None and "cuda" in str(ev.device_type).lower():
+                r = rows.setdefault(ev.name, [0, 0.0])
+                r[0] += 1
+                r[1] += float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0))
+        total = sum(v[1] for v in rows.values())
+        nccl = sum(v[1] for k, v in rows.items() if "nccl" in k.lower())
+        if dump_path and rank == 0:
+            with open(dump_path, "w") as f:
+                f.write("# CUDA kernels of 3 DDP training steps (torch.profiler / CUPTI), rank 0: name, launches, total us\n")
+                for k, v in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                    f.write(f"{v[1]:12.1f} us {v[0]:6d} x  {k[:160]}\n")
+        return {"ms_per_step": nccl / 3e3, "share_of_kernel_time": (nccl / total) if total else None,
+                "kernel_ms_per_step": total / 3e3}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def time_cuda(torch, fn, iters=20, warm=3):
@@ -612,6 +841,21 @@ def measure_extras(torch, pkg, dev, sets, make_set):
     pb = sum(fwd_bytes(B, C, H, W) for (C, H, W) in PYRAMID_384x448)
     out["pyramid5_fwd_B32_384x448"] = {"ms": ms, "pairs_per_s": B / (ms * 1e-3), "GBps": pb / ms / 1e6,
                                        "frac": pb / ms / 1e6 / peak}
+    # the honest per-pair figure of the hot path: all five levels, forward + backward, batch 32
+    for a, b, f in lv:
+        a.requires_grad_(); b.requires_grad_(); f.requires_grad_()
+    gos = [torch.randn(B, 81, H, W, device=dev) for (C, H, W) in PYRAMID_384x448]
+
+    def pyr_fb():
+        for (a, b, f), go in zip(lv, gos):
+            a.grad = b.grad = f.grad = None
+            op(a, b, f).backward(go)
+    ms = time_cuda(torch, pyr_fb, iters=10, warm=2)
+    pbb = pb + sum(bwd_bytes(B, C, H, W) for (C, H, W) in PYRAMID_384x448)
+    out["pyramid5_fwdbwd_B32"] = {"ms": ms, "pairs_per_s": B / (ms * 1e-3), "GBps": pbb / ms / 1e6,
+                                  "frac": pbb / ms / 1e6 / peak,
+                                  "note": "five fused calls of 32 pairs at 384x448, fwd+bwd incl. autograd overhead"}
+    del lv, gos
     # per-level table (north_star: fraction of the HBM roofline at pyramid levels 2-6), forward and
     # backward, literal reference configuration (pad 9 / md 9 / stride2 2) and canonical md=4
     levels = {}
@@ -689,6 +933,29 @@ def measure_extras(torch, pkg, dev, sets, make_set):
                 out["kernels"][f"gpu_reference_fwd_{name}"] = {
                     "ms": ms, "note": "reference correlation_cuda_kernel.cu (unchanged, sm_100a) + its fills + "
                                       "torch grid_sample WarpingLayer port"}
+
+                # forward + backward the way the reference runs it on a GPU: its own kernels for the
+                # correlation and its gradients, torch autograd (grid_sample backward) for the warp
+                def ref_fb():
+                    x2 = f2.detach().requires_grad_()
+                    fl = flow.detach().requires_grad_()
+                    w = tr.warping_layer_port(x2, fl)
+                    with torch.no_grad():
+                        ref_cuda.correlation_forward(f1, w, 4, 1, 4, 1, 1)
+                        _, g2 = ref_cuda.correlation_backward(gout, f1, w.detach(), 4, 1, 4, 1, 1)
+                    w.backward(g2)
+                ms_fb = time_cuda(torch, ref_fb, iters=3, warm=1)
+                out["kernels"][f"gpu_reference_fwdbwd_{name}"] = {
+                    "ms": ms_fb, "pairs_per_s": B / (ms_fb * 1e-3),
+                    "note": "the reference's default GPU path on this B200: its .cu unchanged (2*B backward "
+                            "launches) + torch grid_sample fwd/bwd"}
+            k = out["kernels"]
+            ref_ms = sum(k[f"gpu_reference_fwdbwd_{n}"]["ms"] for n in SHAPES)
+            own_ms = sum(k[f"fwd_{n}_iid"]["ms"] + k[f"bwd_{n}_iid"]["ms"] for n in SHAPES)
+            out["vs_gpu_reference"] = {
+                "reference_ms_per_step": ref_ms, "native_ms_per_step_serial": own_ms, "speedup": ref_ms / own_ms,
+                "note": "cfg2 step (both shapes, fwd+bwd, 32 pairs) on the same B200: reference CUDA kernels + torch "
+                        "grid_sample vs this library, both device-resident and timed back to back on one stream"}
     except Exception as e:   # the bar is optional evidence, never the product path
         out["gpu_reference_error"] = repr(e)
     return out
@@ -719,6 +986,8 @@ def main():
                          "default; every entry point of the library is capturable: no allocation, no sync)")
     ap.add_argument("--graph", action="store_true", help="(default; kept for compatibility)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-kernels", default=None,
+                    help="write the CUPTI kernel list of the DDP training step (rank 0, N > 1) to this file")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not (args.impl == "native" and args.gpus > 1 and world == 1):

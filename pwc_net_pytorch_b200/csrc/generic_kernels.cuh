@@ -254,6 +254,9 @@ warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
     const int HWi = H * W;
     const size_t HW = (size_t)HWi;
     const int t2 = blockIdx.x * blockDim.x + threadIdx.x;
+    // lanes that take part in the pair shuffle at the end: taken while the warp is still converged (the
+    // shuffle names its participants explicitly instead of trusting __activemask() after divergent code)
+    const unsigned pair_mask = __ballot_sync(0xffffffffu, t2 < 2 * HWi);
     if (t2 >= 2 * HWi) return;                        // 2*H*W is even: a lane pair is in or out together
     const int half = t2 & 1;
     const int pix = t2 >> 1;
@@ -267,13 +270,11 @@ warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
     float ax = 0.0f, ay = 0.0f;
     int x0 = 0, y0 = 0;
     const Tap t = make_tap(xx, yy, u, v, H, W, &ax, &ay, &x0, &y0);
-    if (t.off < 0) {                // nothing to scatter, zero flow gradient (the buffers are zeroed)
-        if (warped_out) {
+    const bool live = t.off >= 0;   // else: nothing to scatter, zero flow gradient (the buffers are zeroed)
+    if (!live && warped_out) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (4 * cq + k < C) warped_out[((size_t)n * C + 4 * cq + k) * HW + pix] = 0.0f;
-        }
-        return;
+        for (int k = 0; k < 4; ++k)
+            if (4 * cq + k < C) warped_out[((size_t)n * C + 4 * cq + k) * HW + pix] = 0.0f;
     }
     const bool inx0 = x0 >= 0, inx1 = x0 + 1 < W, iny0 = y0 >= 0, iny1 = y0 + 1 < H;
     const float m00 = (inx0 && iny0) ? 1.0f : 0.0f, m01 = (inx1 && iny0) ? 1.0f : 0.0f;
@@ -284,7 +285,7 @@ warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
     for (int k = 0; k < 4; ++k) {
         const int c = 4 * cq + k;
         g[k] = 0.0f;
-        if (c < C) {
+        if (live && c < C) {
             const size_t plane = ((size_t)n * C + c) * HW;
             g[k] = __ldg(gout + plane + pix);
             const float* p = x + plane + t.off;
@@ -296,7 +297,7 @@ warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                 warped_out[plane + pix] = fmaf(t.w11, v11, fmaf(t.w10, v10, fmaf(t.w01, v01, t.w00 * v00)));
         }
     }
-    if (gx8 && 4 * cq < C) {
+    if (live && gx8 && 4 * cq < C) {
         float* q = gx8 + (((size_t)n * cocts + co) * HW + t.off) * 8 + 4 * half;
         const size_t sdx = (size_t)t.dx * 8, sdy = (size_t)t.dyw * 8;
         if (t.w00 != 0.0f)
@@ -313,11 +314,10 @@ warp_bwd_v8_kernel(const float* __restrict__ gout, const float* __restrict__ x,
                          "f"(g[1] * t.w11), "f"(g[2] * t.w11), "f"(g[3] * t.w11) : "memory");
     }
     if (gflow) {
-        // the two lanes of a pair took the same path up to here (same pixel, same tap)
-        const unsigned mask = __activemask();
-        gu += __shfl_xor_sync(mask, gu, 1);
-        gv += __shfl_xor_sync(mask, gv, 1);
-        if (half == 0) {
+        // every in-range lane reaches this point (no early exit above), dead taps carry zeros
+        gu += __shfl_xor_sync(pair_mask, gu, 1);
+        gv += __shfl_xor_sync(pair_mask, gv, 1);
+        if (half == 0 && live) {
             float* gf = gflow + (size_t)n * 2 * HW + pix;
             if (cocts == 1) {
                 gf[0] = gu;
@@ -349,6 +349,7 @@ deinterleave8_kernel(const float* __restrict__ src8, float* __restrict__ dst, in
         const int c = 8 * co + k;
         if (c < C) dst[((size_t)n * C + c) * HW + pix] = vals[k];
     }
+    griddep_wait();      // see zero2_kernel: explicit ordering when launched into a predecessor's tail
 }
 
 // Zero fill of two float ranges (na, nb multiples of 4, 16-byte aligned bases) as a KERNEL, so that it can
@@ -363,6 +364,11 @@ zero2_kernel(float4* __restrict__ a, size_t na4, float4* __restrict__ b, size_t 
         if (i < na4) a[i] = z;
         else b[i - na4] = z;
     }
+    // launched into the tail of the kernel before it (programmatic dependent launch): this kernel does not
+    // read that kernel's output, but the NEXT kernel in the stream does, and it only waits for this one.
+    // Waiting here -- after our own stores -- makes "this grid complete" imply "the predecessor complete
+    // and flushed" by the PTX rules instead of by driver behaviour; the overlap with the tail is kept.
+    griddep_wait();
 }
 
 // LeakyReLU backward (model.py:84) as a stand-alone pass: dst = grad_out * (out < 0 ? slope : 1).

@@ -226,9 +226,12 @@ bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int 
     return r == CUDA_SUCCESS;
 }
 
-bool tma_eligible(const float* f1, const float* f2, const float* out, const pwc::CorrGeom& g)
+// obs: batch stride (floats) of the tensor the kernel stores to with 128-/256-bit stores; every image's
+// base must be 16-byte aligned, i.e. the stride a multiple of 4 floats (0 = dense)
+bool tma_eligible(const float* f1, const float* f2, const float* out, const pwc::CorrGeom& g, long long obs = 0)
 {
     if (g_disable_tma.load()) return false;
+    if ((obs & 3) != 0) return false;
     if ((g.W & 3) != 0 || g.W < 16 || g.H < 8 || g.W >= 32760 || g.H >= 32760) return false;
     if (((uintptr_t)f1 | (uintptr_t)f2 | (uintptr_t)out) & 15) return false;
     return true;
@@ -306,7 +309,7 @@ int forward_impl(const float* f1, const float* f2, const float* flow, float* out
             return flow ? launch_fwd_small<2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
                         : launch_fwd_small<2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
         }
-        if (tma_eligible(f1, f2, out, g)) {
+        if (tma_eligible(f1, f2, out, g, obs)) {
             int rc;
             if (g.s2 == 1)
                 rc = flow ? launch_fwd_tma<1, 4, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)

@@ -69,4 +69,8 @@ __device__ __forceinline__ float tap_sample(const Tap& t, const float* __restric
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v < 0.0f ? v * slope : v; }
 
+// Programmatic dependent launch: blocks until the grid this one was launched behind has completed and
+// its memory is visible (a no-op for a normally launched kernel).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace pwc

@@ -245,7 +245,9 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
     if (y < H) {
         const float nelems = (float)C;
         const int xs = x0t + ls * PX;
-        const bool vec = ((W & 3) == 0) && (xs + PX <= W) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        // 128-bit stores need every image's base 16-byte aligned: the tensor base AND the batch stride
+        const bool vec = ((W & 3) == 0) && (xs + PX <= W) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                         ((obs & 3) == 0);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             float* o = out + (size_t)n * (size_t)obs + ((size_t)(wd * D + d) * H + y) * W + xs;   // obs: output batch stride

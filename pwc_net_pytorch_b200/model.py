@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import FusedWarpCorrelation
+from .modules import FusedWarpCorrelation, FusedWarpCostVolume
 
 
 def default_args(**overrides):
@@ -107,10 +107,20 @@ class Net(nn.Module):
         self.feature_pyramid_extractor = FeaturePyramidExtractor(args)
         # model.py:24: Correlation(pad = md = 2*search_range+1, kernel 1, stride1 1, stride2 2); the
         # optional leaky_relu_ of model.py:84 (slope 0.01) is the kernel's epilogue
-        self.warp_corr = ops if ops is not None else FusedWarpCorrelation.from_search_range(
-            args.search_range, activation=bool(args.corr_activation), negative_slope=0.01, return_warped=True)
+        # model.py:21-22: `--corr CostVolumeLayer` selects the pure-PyTorch layer, which samples +-search_range
+        # at stride 1, orders its channels axis-first and divides by 81 -- a different volume from the CUDA
+        # op's, so a checkpoint trained with it needs exactly that volume
+        cost_volume_layer = getattr(args, "corr", None) == "CostVolumeLayer"
+        if ops is not None:
+            self.warp_corr = ops
+        elif cost_volume_layer:
+            self.warp_corr = FusedWarpCostVolume(args.search_range, activation=bool(args.corr_activation),
+                                                 negative_slope=0.01, return_warped=True)
+        else:
+            self.warp_corr = FusedWarpCorrelation.from_search_range(
+                args.search_range, activation=bool(args.corr_activation), negative_slope=0.01, return_warped=True)
         self._own_ops = ops is None
-        self._direct_concat = ops is None and args.search_range == 4
+        self._direct_concat = ops is None and args.search_range == 4 and not cost_volume_layer
         self.flow_estimators = []
         for l, ch in enumerate(args.lv_chs[::-1] + [3]):
             est = OpticalFlowEstimator(args, ch + (args.search_range * 2 + 1) ** 2 + 2)

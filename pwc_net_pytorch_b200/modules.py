@@ -3,6 +3,7 @@
   WarpingLayer(args).forward(x, flow)      modules.py:25-42 -- same constructor and call
   FusedWarpCorrelation(...)(x1, x2, flow)  model.py:80-84 in one launch (new entry point)
 """
+import torch
 import torch.nn as nn
 
 from . import functional as PF
@@ -57,3 +58,43 @@ class FusedWarpCorrelation(nn.Module):
         return PF.warp_correlation(x1, x2, flow, self.pad_size, self.kernel_size,
                                    self.max_displacement, self.stride1, self.stride2,
                                    self.activation, self.negative_slope, self.return_warped)
+
+
+def cost_volume_channel_order(search_range):
+    """Raster channel tc = (dy + r) * D + (dx + r) of `Correlation(pad r, md r, stride2 1)` that holds
+    channel I of the reference's pure-PyTorch `CostVolumeLayer` (modules.py:58-72): (0, 0) first, then for
+    i = 1..r the axis displacements (-i,0), (+i,0), (0,-i), (0,+i) followed, for j = 1..r, by the diagonal
+    ones (-i,-j), (+i,+j), (-i,+j), (+i,-j)."""
+    r = search_range
+    D = 2 * r + 1
+    order = [(0, 0)]
+    for i in range(1, r + 1):
+        order += [(-i, 0), (i, 0), (0, -i), (0, i)]
+        for j in range(1, r + 1):
+            order += [(-i, -j), (i, j), (-i, j), (i, -j)]
+    return [(dy + r) * D + (dx + r) for dy, dx in order]
+
+
+class FusedWarpCostVolume(nn.Module):
+    """`CostVolumeLayer(x1, WarpingLayer(x2, flow))` of the reference (modules.py:45-74, selected by
+    `--corr CostVolumeLayer`, model.py:21-22) on the same fused kernel: displacements +-search_range at
+    stride 1, the layer's own channel order, and division by D*D instead of by C (SURVEY.md section 0
+    fact 5).  The LeakyReLU of model.py:84 commutes with the positive rescale, so it stays in the kernel's
+    epilogue; the permutation + rescale is one gather pass over the 81 channels."""
+
+    def __init__(self, search_range=4, activation=False, negative_slope=0.01, return_warped=False):
+        super(FusedWarpCostVolume, self).__init__()
+        self.search_range = search_range
+        self.return_warped = return_warped
+        self.op = FusedWarpCorrelation(pad_size=search_range, kernel_size=1, max_displacement=search_range,
+                                       stride1=1, stride2=1, activation=activation,
+                                       negative_slope=negative_slope, return_warped=return_warped)
+        self.register_buffer("order", torch.tensor(cost_volume_channel_order(search_range), dtype=torch.long),
+                             persistent=False)
+
+    def forward(self, x1, x2, flow=None):
+        res = self.op(x1, x2, flow)
+        corr, warped = res if self.return_warped else (res, None)
+        D2 = (2 * self.search_range + 1) ** 2
+        corr = corr.index_select(1, self.order.to(corr.device)) * (float(x1.size(1)) / D2)
+        return (corr, warped) if self.return_warped else corr

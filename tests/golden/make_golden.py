@@ -9,6 +9,7 @@ What it pins (the reference ships no tests or golden vectors of its own, SURVEY.
     F.grid_sample is called with align_corners=True, which is what torch 0.4.0
     (requirements.txt:62) did and what the reference was written against (SURVEY.md section 0
     fact 3); torch 2.x changed the default.
+  * its backward: gradients w.r.t. x and flow from torch autograd through that unmodified forward.
   * modules.CostVolumeLayer (modules.py:45-74) imported unmodified; it equals the CUDA
     Correlation(pad=4, kernel=1, md=4, stride1=1, stride2=1) up to the channel permutation of
     SURVEY.md appendix B and the factor C/81, which pins the channel order / displacement sign of
@@ -77,6 +78,15 @@ def main():
         out[f"{name}/warp"] = w.numpy()
         out[f"{name}/costvolume_plain"] = cv_plain.numpy()
         out[f"{name}/costvolume_of_warp"] = cv_warp.numpy()
+        # autograd of the reference's own WarpingLayer.forward (grid_sample backward + the gradient of
+        # modules.py:36-40): pins the warp *backward*  to reference code
+        gw = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        x2 = torch.from_numpy(f2).clone().requires_grad_()
+        fl = torch.from_numpy(flow).clone().requires_grad_()
+        warp(x2, fl).backward(torch.from_numpy(gw))
+        out[f"{name}/warp_gout"] = gw
+        out[f"{name}/warp_gx"] = x2.grad.numpy()
+        out[f"{name}/warp_gflow"] = fl.grad.numpy()
     # zero flow must be the identity under the 0.4.0 semantics
     z = torch.zeros(1, 2, 6, 7)
     x = torch.from_numpy(out["tiny/f2"][:1])

@@ -120,3 +120,13 @@ def test_header_compiles_as_plain_c_and_links(tmp_path):
     p = subprocess.run([str(exe)], capture_output=True, text=True)
     assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
     assert "kernel_size" in p.stdout
+
+
+def test_cost_volume_channel_order_is_the_reference_layers():
+    """`--corr CostVolumeLayer` (model.py:21-22): the channel order the product uses to turn the fused
+    kernel's raster volume into the layer's own order (modules.py:58-72) equals the permutation the
+    oracle derived from the reference-authored golden outputs."""
+    from oracle import torch_ref as tr
+    from pwc_net_pytorch_b200.modules import cost_volume_channel_order
+    assert cost_volume_channel_order(4) == [int(v) for v in tr.COSTVOLUME_PERM]
+    assert sorted(cost_volume_channel_order(3)) == list(range(49))
