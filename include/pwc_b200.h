@@ -45,7 +45,7 @@ extern "C" {
 typedef struct CUstream_st *cudaStream_t;
 #endif
 
-#define PWC_B200_ABI_VERSION 3
+#define PWC_B200_ABI_VERSION 4
 
 /* ---- legacy launchers: correlation_cuda_kernel.h:5-39 ------------------------------------- */
 int Correlation_forward_cuda_kernel(
@@ -104,6 +104,23 @@ int pwc_warpcorr_forward_strided(const float *f1, const float *f2, const float *
                                  int pad_size, int kernel_size, int max_displacement,
                                  int stride1, int stride2,
                                  int act, float slope, cudaStream_t stream);
+
+/* ---- same, with model.py:78 folded in: the flow is given at the previous (coarser) pyramid level,
+ * coarse_flow:[B,2,H/2,W/2] dense (H, W even), and the kernel itself evaluates
+ *     flow = F.upsample(coarse_flow, scale_factor=2, mode='bilinear') * 2        (align_corners=False)
+ * bit for bit as torch does, warps input2 by it, and writes it to flow_out (required: the flow estimator
+ * takes the fine flow as an input, model.py:89-91): image n's [2,H,W] block at flow_out +
+ * n * flow_out_batch_stride floats (0 = dense) -- typically the last two channels of the estimator's
+ * concatenated input, next to the cost volume written through out / out_batch_stride.
+ * Replaces one F.upsample launch, one multiply launch and a [B,2,H,W] round trip per pyramid level.
+ * Forward only (inference); training keeps the flow as a tensor and uses pwc_warpcorr_forward. ------- */
+int pwc_warpcorr_forward_coarse(const float *f1, const float *f2, const float *coarse_flow,
+                                float *out, long long out_batch_stride,
+                                float *flow_out, long long flow_out_batch_stride, float *warped_out,
+                                int B, int C, int H, int W,
+                                int pad_size, int kernel_size, int max_displacement,
+                                int stride1, int stride2,
+                                int act, float slope, cudaStream_t stream);
 
 /* ---- backward of pwc_warpcorr_forward.
  * out        : the forward result, read only when act != 0 (sign gate of leaky_relu_).

@@ -28,6 +28,7 @@ EXPORTS = (
     "pwc_warp_backward",
     "pwc_warpcorr_forward",
     "pwc_warpcorr_forward_strided",
+    "pwc_warpcorr_forward_coarse",
     "pwc_warpcorr_backward_workspace",
     "pwc_warpcorr_backward",
     "pwc_last_error",
@@ -62,6 +63,9 @@ def _declare(L):
     L.pwc_warpcorr_forward_strided.argtypes = ([_c_float_p] * 4 + [ctypes.c_longlong, _c_float_p] + [_int] * 9 +
                                                [_int, ctypes.c_float] + [_stream])
     L.pwc_warpcorr_forward_strided.restype = _int
+    L.pwc_warpcorr_forward_coarse.argtypes = ([_c_float_p] * 4 + [ctypes.c_longlong, _c_float_p, ctypes.c_longlong,
+                                               _c_float_p] + [_int] * 9 + [_int, ctypes.c_float] + [_stream])
+    L.pwc_warpcorr_forward_coarse.restype = _int
     L.pwc_warpcorr_backward_workspace.argtypes = [_int] * 10
     L.pwc_warpcorr_backward_workspace.restype = ctypes.c_longlong
     L.pwc_warpcorr_backward.argtypes = ([_c_float_p] * 9 + [ctypes.c_void_p, ctypes.c_longlong] +
@@ -96,7 +100,7 @@ def load():
                     "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
             L = ctypes.CDLL(LIB_PATH)
             _declare(L)
-            if L.pwc_abi_version() != 3:
+            if L.pwc_abi_version() != 4:
                 raise RuntimeError("libpwc_b200.so ABI version mismatch; rebuild it")
             _lib = L
     return _lib

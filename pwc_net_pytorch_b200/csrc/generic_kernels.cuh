@@ -44,7 +44,7 @@ __device__ __forceinline__ float first_operand(const float* __restrict__ f1n, in
 __global__ void __launch_bounds__(256)
 corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                         const float* __restrict__ flow, float* __restrict__ out, CorrGeom g,
-                        int act, float slope, long long obs)
+                        int act, float slope, long long obs, long long fbs)
 {
     const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +59,7 @@ corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ 
     const size_t HW = (size_t)g.H * g.W;
     const float* f1n = f1 + (size_t)n * g.C * HW;
     const float* f2n = f2 + (size_t)n * g.C * HW;
-    const float* flown = flow ? flow + (size_t)n * 2 * HW : nullptr;
+    const float* flown = flow ? flow + (size_t)n * (size_t)fbs : nullptr;   // fbs: flow batch stride
     float s = 0.0f;
     for (int j = -g.kr; j <= g.kr; ++j)
         for (int i = -g.kr; i <= g.kr; ++i)
@@ -69,6 +69,27 @@ corr_fwd_generic_kernel(const float* __restrict__ f1, const float* __restrict__ 
     float v = s / (float)(g.k * g.k * g.C);
     if (act) v = leaky(v, slope);
     out[(size_t)n * (size_t)obs + (idx - (size_t)n * g.oc * g.oh * g.ow)] = v;   // obs: output batch stride
+}
+
+// model.py:78 as a stand-alone pass: fine = F.upsample(coarse, 2, 'bilinear') * 2, written with a batch stride
+// (image n's [2][H][W] block starts at fine + n * fobs -- the last two channels of the flow estimator's
+// concatenated input).  Used where the fold into the fused kernel's flow read does not apply.
+__global__ void __launch_bounds__(256)
+flow_up2_kernel(const float* __restrict__ coarse, float* __restrict__ fine, long long fobs, int B, int H, int W)
+{
+    const int Hc = H >> 1, Wc = W >> 1;
+    const size_t HW = (size_t)H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * HW) return;
+    const int n = (int)(idx / HW);
+    const int pix = (int)(idx - (size_t)n * HW);
+    const int y = pix / W, x = pix - y * W;
+    const float* cu = coarse + (size_t)n * 2 * Hc * Wc;
+    float u, v;
+    up2_flow_at(cu, cu + (size_t)Hc * Wc, Hc, Wc, x, y, u, v);
+    float* o = fine + (size_t)n * (size_t)fobs + pix;
+    o[0] = u;
+    o[HW] = v;
 }
 
 // correlation_cuda_kernel.cu:119-196 (gradInput1) and :211-288 (gradInput2) for stride1 == 1,

@@ -71,8 +71,21 @@ bool fast_path(const pwc::CorrGeom& g)
            (g.s2 == 1 || g.s2 == 2);
 }
 
+// Where the forward kernels take the flow from (model.py:74-80):
+//   flow   : [2][H][W] per image, image n at flow + n * fbs floats (fbs == 2*H*W when dense), or NULL (no warp)
+//   coarse : when non-NULL, the previous level's flow [B][2][H/2][W/2] (dense); the kernel evaluates
+//            model.py:78 itself (flow = F.upsample(coarse, 2, 'bilinear') * 2) and writes the fine flow to
+//            flow_out + n * fobs.  Kernels without the fold are given flow = flow_out after a prepass.
+struct FlowSpec {
+    const float* flow;
+    long long fbs;
+    const float* coarse;
+    float* flow_out;
+    long long fobs;
+};
+
 template <class Cfg, bool HAS_FLOW>
-int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
+int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, long long fbs, float* out,
                      float* warped, const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     auto kern = pwc::warpcorr_fwd_kernel<Cfg, HAS_FLOW>;
@@ -106,7 +119,7 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, float*
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (cudaLaunchKernelEx(&cfg, kern, f1, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, act, slope,
-                           ksplit, cper, obs) != cudaSuccess)
+                           ksplit, cper, obs, fbs) != cudaSuccess)
         return fail("warpcorr_fwd_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     return check_launch("warpcorr_fwd_kernel");
 }
@@ -172,12 +185,12 @@ int launch_small(Kern kern, const char* what, size_t smem, int B, int ks, cudaSt
 }
 
 template <int S2, bool HAS_FLOW>
-int launch_fwd_small(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+int launch_fwd_small(const float* f1, const float* f2, const FlowSpec& fs, float* out, float* warped,
                      const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     const pwc::SmallPlan p = small_plan_for(g, HAS_FLOW, false);
-    return launch_small(pwc::warpcorr_fwd_small_kernel<S2, HAS_FLOW>, "warpcorr_fwd_small_kernel", p.smem, g.B, p.ks, st, f1, f2, flow, out, warped, g.C, g.H,
-                        g.W, p.cs, p.csp, act, slope, obs);
+    return launch_small(pwc::warpcorr_fwd_small_kernel<S2, HAS_FLOW>, "warpcorr_fwd_small_kernel", p.smem, g.B, p.ks, st, f1, f2, fs.flow, out, warped, g.C, g.H,
+                        g.W, p.cs, p.csp, act, slope, obs, fs.fbs, fs.coarse, fs.flow_out, fs.fobs);
 }
 
 template <int S2, bool HAS_FLOW>
@@ -212,12 +225,16 @@ EncodeTiledFn encode_tiled_fn()
 
 // 4-D tensor map over a dense [B][C][H][W] fp32 tensor, box = (bw, bh, bc, 1); out-of-range box
 // elements (image border, channel tail) are filled with zeros by the TMA unit.
-bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int W, int bw, int bh, int bc)
+// batch_stride: floats between consecutive images (0 = dense, C*H*W); must be a multiple of 4 floats.
+bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int W, int bw, int bh, int bc,
+                   long long batch_stride = 0)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
+    if (batch_stride == 0) batch_stride = (long long)W * H * C;
+    if ((batch_stride & 3) != 0 || ((W * 4) & 15) != 0) return false;      // TMA global strides are multiples of 16 bytes
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)batch_stride * 4};
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
@@ -239,18 +256,24 @@ bool tma_eligible(const float* f1, const float* f2, const float* out, const pwc:
 
 // returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
 template <int S2, int CK, bool HAS_FLOW>
-int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+int launch_fwd_tma(const float* f1, const float* f2, const FlowSpec& fs, float* out, float* warped,
                    const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     using Cfg = pwc::TmaCfg<S2, CK>;
+    const float* flow = fs.flow;
     CUtensorMap m1, m2;
     if (!make_nchw_map(&m1, f1, g.B, g.C, g.H, g.W, Cfg::F1W, Cfg::F1H, CK)) return -1;
     if (!make_nchw_map(&m2, f2, g.B, g.C, g.H, g.W, HAS_FLOW ? Cfg::WW : Cfg::WP, HAS_FLOW ? Cfg::WH : Cfg::HH, CK))
         return -1;
     CUtensorMap m3 = m2;   // unused without flow
     if (HAS_FLOW) {
-        if (((uintptr_t)flow & 15) != 0) return -1;
-        if (!make_nchw_map(&m3, flow, g.B, 2, g.H, g.W, Cfg::HWD, Cfg::HH, 2)) return -1;
+        if (fs.coarse) {   // model.py:78 folded into the flow read: the map covers the coarse flow
+            if (((uintptr_t)fs.coarse & 15) != 0 || (g.H & 1) || (g.W & 7)) return -1;
+            if (!make_nchw_map(&m3, fs.coarse, g.B, 2, g.H / 2, g.W / 2, Cfg::CWB, Cfg::CHB, 2)) return -1;
+        } else {
+            if (((uintptr_t)flow & 15) != 0) return -1;
+            if (!make_nchw_map(&m3, flow, g.B, 2, g.H, g.W, Cfg::HWD, Cfg::HH, 2, fs.fbs)) return -1;
+        }
     }
     auto kern = pwc::warpcorr_fwd_tma_kernel<Cfg, HAS_FLOW>;
     const size_t smem = Cfg::smem_bytes(HAS_FLOW);
@@ -272,63 +295,97 @@ int launch_fwd_tma(const float* f1, const float* f2, const float* flow, float* o
     // persistent: one CTA per SM (148 on B200), each walks tiles blockIdx.x, blockIdx.x + grid, ...
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     kern<<<grid, Cfg::NT, smem, st>>>(m1, m2, m3, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles,
-                                      act, slope, obs);
+                                      act, slope, obs, fs.fbs, fs.coarse, fs.flow_out, fs.fobs);
     return check_launch("warpcorr_fwd_tma_kernel");
 }
 
 template <int S2, bool HAS_FLOW>
-int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, float* out,
+int dispatch_fwd_tiled(const float* f1, const float* f2, const float* flow, long long fbs, float* out,
                        float* warped, const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     if (g.W > 16)
-        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 8, 4, 8>, HAS_FLOW>(f1, f2, flow, fbs, out, warped, g, act, slope, obs, st);
     // small images (6x7, 12x14 levels: few CTAs, many channels): deep channel chunks, so that the
     // serial chunk loop is short and each chunk keeps many gathers in flight
     if (g.C >= 64)
-        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, (S2 == 1 ? 28 : 16)>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
-    return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+        return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, (S2 == 1 ? 28 : 16)>, HAS_FLOW>(f1, f2, flow, fbs, out, warped, g, act, slope, obs, st);
+    return launch_fwd_tiled<pwc::FwdCfg<9, S2, 4, 4, 8>, HAS_FLOW>(f1, f2, flow, fbs, out, warped, g, act, slope, obs, st);
 }
 
-int forward_impl(const float* f1, const float* f2, const float* flow, float* out, float* warped,
+// model.py:78 as its own launch (where the fold into the fused kernel does not apply): fs.coarse -> fs.flow_out,
+// after which the flow is an ordinary strided input.
+int flow_prepass(FlowSpec& fs, const pwc::CorrGeom& g, cudaStream_t st)
+{
+    const size_t total = (size_t)g.B * g.H * g.W;
+    pwc::flow_up2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(fs.coarse, fs.flow_out, fs.fobs, g.B, g.H, g.W);
+    if (!check_launch("flow_up2_kernel")) return 0;
+    fs.flow = fs.flow_out;
+    fs.fbs = fs.fobs;
+    fs.coarse = nullptr;
+    return 1;
+}
+
+int forward_impl(const float* f1, const float* f2, FlowSpec fs, float* out, float* warped,
                  const pwc::CorrGeom& g, int act, float slope, long long obs, cudaStream_t st)
 {
     const long long dense = (long long)g.oc * g.oh * g.ow;
     if (obs == 0) obs = dense;
     if (obs < dense) return fail("output batch stride %lld is smaller than one image's output (%lld)", obs, dense);
+    const long long fdense = 2LL * g.H * g.W;
+    if (fs.fbs == 0) fs.fbs = fdense;
+    if (fs.fobs == 0) fs.fobs = fdense;
+    if (fs.flow && fs.fbs < fdense) return fail("flow batch stride %lld is smaller than one image's flow (%lld)", fs.fbs, fdense);
+    if (fs.coarse) {
+        if ((g.H & 1) || (g.W & 1)) return fail("coarse flow: H and W must be even (got %d x %d)", g.H, g.W);
+        if (!fs.flow_out) return fail("coarse flow: flow_out is required (the flow estimator needs the fine flow)");
+        if (fs.fobs < fdense) return fail("flow_out batch stride %lld is smaller than one image's flow (%lld)", fs.fobs, fdense);
+    }
+    const bool has_flow = fs.flow != nullptr || fs.coarse != nullptr;
     if (fast_path(g)) {
-        if (warped && !flow) {   // no warp: x2_warp is x2 itself (model.py:80 with zero displacement)
+        if (warped && !has_flow) {   // no warp: x2_warp is x2 itself (model.py:80 with zero displacement)
             if (cudaMemcpyAsync(warped, f2, sizeof(float) * (size_t)g.B * g.C * g.H * g.W,
                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess)
                 return fail("cudaMemcpyAsync(warped_out): %s", cudaGetErrorString(cudaGetLastError()));
             warped = nullptr;
         }
-        if (small_plan_for(g, flow != nullptr, false).ok) {
+        if (small_plan_for(g, has_flow, false).ok) {      // folds the coarse flow itself
             if (g.s2 == 1)
-                return flow ? launch_fwd_small<1, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                            : launch_fwd_small<1, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
-            return flow ? launch_fwd_small<2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                        : launch_fwd_small<2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+                return has_flow ? launch_fwd_small<1, true>(f1, f2, fs, out, warped, g, act, slope, obs, st)
+                                : launch_fwd_small<1, false>(f1, f2, fs, out, warped, g, act, slope, obs, st);
+            return has_flow ? launch_fwd_small<2, true>(f1, f2, fs, out, warped, g, act, slope, obs, st)
+                            : launch_fwd_small<2, false>(f1, f2, fs, out, warped, g, act, slope, obs, st);
         }
-        if (tma_eligible(f1, f2, out, g, obs)) {
+        if (tma_eligible(f1, f2, out, g, obs)) {          // folds it when W % 8 == 0 (TMA stride rule), else -1
             int rc;
             if (g.s2 == 1)
-                rc = flow ? launch_fwd_tma<1, 4, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                          : launch_fwd_tma<1, 4, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+                rc = has_flow ? launch_fwd_tma<1, 4, true>(f1, f2, fs, out, warped, g, act, slope, obs, st)
+                              : launch_fwd_tma<1, 4, false>(f1, f2, fs, out, warped, g, act, slope, obs, st);
             else
-                rc = flow ? launch_fwd_tma<2, 2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                          : launch_fwd_tma<2, 2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+                rc = has_flow ? launch_fwd_tma<2, 2, true>(f1, f2, fs, out, warped, g, act, slope, obs, st)
+                              : launch_fwd_tma<2, 2, false>(f1, f2, fs, out, warped, g, act, slope, obs, st);
             if (rc >= 0) return rc;
+            if (fs.coarse) {                              // not foldable here: prepass, then the TMA kernel again
+                if (!flow_prepass(fs, g, st)) return 0;
+                rc = g.s2 == 1 ? launch_fwd_tma<1, 4, true>(f1, f2, fs, out, warped, g, act, slope, obs, st)
+                               : launch_fwd_tma<2, 2, true>(f1, f2, fs, out, warped, g, act, slope, obs, st);
+                if (rc >= 0) return rc;
+            }
         }
+        if (fs.coarse && !flow_prepass(fs, g, st)) return 0;
+        const float* flow = fs.flow;
         if (g.s2 == 1)
-            return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                        : dispatch_fwd_tiled<1, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
-        return flow ? dispatch_fwd_tiled<2, true>(f1, f2, flow, out, warped, g, act, slope, obs, st)
-                    : dispatch_fwd_tiled<2, false>(f1, f2, flow, out, warped, g, act, slope, obs, st);
+            return flow ? dispatch_fwd_tiled<1, true>(f1, f2, flow, fs.fbs, out, warped, g, act, slope, obs, st)
+                        : dispatch_fwd_tiled<1, false>(f1, f2, flow, fs.fbs, out, warped, g, act, slope, obs, st);
+        return flow ? dispatch_fwd_tiled<2, true>(f1, f2, flow, fs.fbs, out, warped, g, act, slope, obs, st)
+                    : dispatch_fwd_tiled<2, false>(f1, f2, flow, fs.fbs, out, warped, g, act, slope, obs, st);
     }
+    if (fs.coarse && !flow_prepass(fs, g, st)) return 0;
+    const float* flow = fs.flow;
     const size_t total = (size_t)g.B * g.oc * g.oh * g.ow;
-    pwc::corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f1, f2, flow, out, g, act, slope, obs);
+    pwc::corr_fwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f1, f2, flow, out, g, act, slope, obs, fs.fbs);
     if (!check_launch("corr_fwd_generic_kernel")) return 0;
     if (warped) {
+        if (flow && fs.fbs != fdense) return fail("warped_out with a strided flow is only available on the 81-displacement fast path");
         if (flow) return pwc_warp_forward(f2, flow, warped, g.B, g.C, g.H, g.W, st);
         if (cudaMemcpyAsync(warped, f2, sizeof(float) * (size_t)g.B * g.C * g.H * g.W,
                             cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -656,7 +713,7 @@ int pwc_warpcorr_forward(const float* f1, const float* f2, const float* flow, fl
     if (!f1 || !f2 || !out) return fail("pwc_warpcorr_forward: null pointer");
     pwc::CorrGeom g;
     if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
-    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, 0, stream);
+    return forward_impl(f1, f2, FlowSpec{flow, 0, nullptr, nullptr, 0}, out, warped_out, g, act, slope, 0, stream);
 }
 
 int pwc_warpcorr_forward_strided(const float* f1, const float* f2, const float* flow, float* out,
@@ -667,7 +724,20 @@ int pwc_warpcorr_forward_strided(const float* f1, const float* f2, const float* 
     if (!f1 || !f2 || !out) return fail("pwc_warpcorr_forward_strided: null pointer");
     pwc::CorrGeom g;
     if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
-    return forward_impl(f1, f2, flow, out, warped_out, g, act, slope, out_batch_stride, stream);
+    return forward_impl(f1, f2, FlowSpec{flow, 0, nullptr, nullptr, 0}, out, warped_out, g, act, slope, out_batch_stride, stream);
+}
+
+int pwc_warpcorr_forward_coarse(const float* f1, const float* f2, const float* coarse_flow, float* out,
+                                long long out_batch_stride, float* flow_out, long long flow_out_batch_stride,
+                                float* warped_out, int B, int C, int H, int W, int pad_size, int kernel_size,
+                                int max_displacement, int stride1, int stride2, int act, float slope,
+                                cudaStream_t stream)
+{
+    if (!f1 || !f2 || !out || !coarse_flow || !flow_out) return fail("pwc_warpcorr_forward_coarse: null pointer");
+    pwc::CorrGeom g;
+    if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
+    return forward_impl(f1, f2, FlowSpec{nullptr, 0, coarse_flow, flow_out, flow_out_batch_stride}, out, warped_out, g,
+                        act, slope, out_batch_stride, stream);
 }
 
 long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_flow, int, int, int,
@@ -745,7 +815,7 @@ int Correlation_forward_cuda_kernel(float* output, int ob, int oc, int oh, int o
     if (oc != g.oc || oh != g.oh || ow != g.ow)
         return fail("output is [%d,%d,%d,%d] but the parameters give [%d,%d,%d,%d]", ob, oc, oh, ow,
                     ob, g.oc, g.oh, g.ow);
-    return forward_impl(input1, input2, nullptr, output, nullptr, g, 0, 0.0f, 0, stream);
+    return forward_impl(input1, input2, FlowSpec{nullptr, 0, nullptr, nullptr, 0}, output, nullptr, g, 0, 0.0f, 0, stream);
 }
 
 int Correlation_backward_cuda_kernel(float* gradOutput, int gob, int goc, int goh, int gow, int,

@@ -69,6 +69,38 @@ __device__ __forceinline__ float tap_sample(const Tap& t, const float* __restric
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v < 0.0f ? v * slope : v; }
 
+// ---- model.py:78: flow = F.upsample(flow_coarse, scale_factor=2, mode='bilinear') * 2, folded into the flow read.
+// F.upsample(bilinear) is align_corners=False in torch 0.4.0 and 2.x alike.  The
+// arithmetic below is ATen's upsample_bilinear2d_out_frame as compiled for sm_100 (read from the SASS of torch
+// 2.11's libtorch_cuda.so): source index s = max(fma(i + 0.5, 0.5, -0.5), 0), i0 = (int)s, i1 = i0 + (i0 < n-1),
+// lambda1 = s - i0, lambda0 = 1 - lambda1; a blend a*l0 + b*l1 is evaluated as fma(l0, a, l1*b) with the second
+// product rounded on its own, for the horizontal and then the vertical pair; `* 2` is exact.  The result equals
+// `F.interpolate(c, scale_factor=2, mode='bilinear', align_corners=False) * 2` bit for bit.
+__device__ __forceinline__ float up2_source(int i, int n_coarse, int& i0, int& i1)
+{
+    const float s = fmaxf(__fmaf_rn((float)i + 0.5f, 0.5f, -0.5f), 0.0f);
+    i0 = (int)s;
+    i1 = i0 + (i0 < n_coarse - 1 ? 1 : 0);
+    return s - (float)i0;
+}
+__device__ __forceinline__ float up2_blend(float v00, float v01, float v10, float v11, float lx1, float ly1)
+{
+    const float lx0 = 1.0f - lx1, ly0 = 1.0f - ly1;
+    const float top = __fmaf_rn(lx0, v00, __fmul_rn(lx1, v01));
+    const float bot = __fmaf_rn(lx0, v10, __fmul_rn(lx1, v11));
+    return __fmul_rn(2.0f, __fmaf_rn(ly0, top, __fmul_rn(ly1, bot)));
+}
+// (u, v) of fine pixel (x, y) from image n's coarse flow planes cu, cv ([Hc][Wc] each), through global memory
+__device__ __forceinline__ void up2_flow_at(const float* __restrict__ cu, const float* __restrict__ cv, int Hc,
+                                            int Wc, int x, int y, float& u, float& v)
+{
+    int x0, x1, y0, y1;
+    const float lx1 = up2_source(x, Wc, x0, x1), ly1 = up2_source(y, Hc, y0, y1);
+    const int a = y0 * Wc + x0, b = y0 * Wc + x1, c = y1 * Wc + x0, d = y1 * Wc + x1;
+    u = up2_blend(__ldg(cu + a), __ldg(cu + b), __ldg(cu + c), __ldg(cu + d), lx1, ly1);
+    v = up2_blend(__ldg(cv + a), __ldg(cv + b), __ldg(cv + c), __ldg(cv + d), lx1, ly1);
+}
+
 // Programmatic dependent launch: blocks until the grid this one was launched behind has completed and
 // its memory is visible (a no-op for a normally launched kernel).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -71,8 +71,12 @@ __global__ void __launch_bounds__(SMALL_NT)
 warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                           const float* __restrict__ flow, float* __restrict__ out,
                           float* __restrict__ warped_out, int C, int H, int W, int cs, int csp, int act,
-                          float slope, long long obs)
+                          float slope, long long obs, long long fbs, const float* __restrict__ coarse,
+                          float* __restrict__ flow_out, long long fobs)
 {
+    // flow source: `flow` ([2][H][W] per image, batch stride fbs), or -- model.py:78 folded into this read --
+    // `coarse` ([B][2][H/2][W/2], dense): flow = F.upsample(coarse, 2, 'bilinear') * 2, which rank 0 of the
+    // cluster also writes to flow_out (batch stride fobs) because the flow estimator needs it as a tensor
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int D = 9, r = 4, NT = SMALL_NT;
@@ -96,10 +100,24 @@ warpcorr_fwd_small_kernel(const float* __restrict__ f1, const float* __restrict_
     const float* f2n = f2 + ((size_t)n * C + c_begin) * HW;
 
     if (HAS_FLOW) {
-        const float* un = flow + (size_t)n * 2 * HW;
+        const float* un = coarse ? nullptr : flow + (size_t)n * (size_t)fbs;
+        const int Hc = H >> 1, Wc = W >> 1;
+        const float* cu = coarse ? coarse + (size_t)n * 2 * Hc * Wc : nullptr;
         for (int q = tid; q < HW; q += NT) {
             const int y = q / W, x = q - y * W;
-            const Tap tp = make_tap(x, y, __ldg(un + q), __ldg(un + HW + q), H, W);
+            float u, v;
+            if (coarse) {
+                up2_flow_at(cu, cu + Hc * Wc, Hc, Wc, x, y, u, v);
+                if (rank == 0 && flow_out != nullptr) {
+                    float* fo = flow_out + (size_t)n * (size_t)fobs + q;
+                    fo[0] = u;
+                    fo[HW] = v;
+                }
+            } else {
+                u = __ldg(un + q);
+                v = __ldg(un + HW + q);
+            }
+            const Tap tp = make_tap(x, y, u, v, H, W);
             sTapW[q] = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
             sTapO[q] = make_int2(tp.off, (tp.dyw << 1) | tp.dx);
         }

@@ -76,7 +76,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                     const float* __restrict__ flow, float* __restrict__ out,
                     float* __restrict__ warped_out,
                     int C, int H, int W, int tiles_x, int tiles_y, int act, float slope, int ksplit, int cper,
-                    long long obs)
+                    long long obs, long long fbs)
 {
     // ksplit > 1: the kernel is launched in thread-block clusters of ksplit CTAs; the CTAs of a cluster
     // share one tile and split its channels (cper each); partial accumulators are summed through
@@ -108,7 +108,7 @@ warpcorr_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
     const float* f2n = f2 + (size_t)n * C * HW;
 
     if (HAS_FLOW) {
-        const float* un = flow + (size_t)n * 2 * HW;
+        const float* un = flow + (size_t)n * (size_t)fbs;      // fbs: flow batch stride
         for (int i = tid; i < NHALO; i += NT) {
             const int hy = i / HWD, hx = i - hy * HWD;
             const int y = y0t - R + hy, x = x0t - R + hx;

@@ -120,6 +120,15 @@ struct TmaCfg {
     static constexpr int FLOW_ELEMS = 2 * HH * HWD;        // flow tile + halo (u and v), TMA box
     static constexpr uint32_t WIN_BYTES = WIN_ELEMS * 4, F1_BYTES = F1_ELEMS * 4, W2_BYTES = W2_ELEMS * 4;
     static constexpr uint32_t FLOW_BYTES = FLOW_ELEMS * 4;
+    // model.py:78 folded into the flow read: instead of the fine flow tile + halo the T warp fetches the
+    // coarse flow's [CHB][CWB] box around it (per component) and the P warp evaluates 2 * bilinear-up2 from
+    // shared memory.  Fine columns x0-R .. x0+TW+R-1 need coarse columns x0/2 - R/2 - 1 .. x0/2 + (TW+R)/2;
+    // the box starts CW_OFF (a multiple of 4: 16-byte aligned TMA start, see WW) left of x0/2.
+    static constexpr int CW_OFF = (R / 2 + 1 + 3) / 4 * 4, CH_OFF = R / 2 + 1;
+    static constexpr int CWB = (CW_OFF + (TW + R) / 2 + 1 + 3) / 4 * 4, CHB = CH_OFF + (TH + R) / 2 + 1;
+    static constexpr uint32_t CFLOW_BYTES = 2 * CHB * CWB * 4;
+    static_assert(2 * CHB * CWB <= FLOW_ELEMS, "the coarse flow box reuses the fine flow tile's buffer");
+    static_assert(TW % 8 == 0 && TH % 2 == 0 && R % 2 == 0, "tile origins must halve to multiples of 4 / integers");
     static constexpr int NBARS = 2 * NF1 + 2 * NS + 2 * NWIN + 8;
     static constexpr int CTRL_BYTES = 512;                 // mbarriers + window origins
     static_assert(WP % 8 == 4 && F1W % 8 == 4, "pitches must be 4 mod 8 floats");
@@ -181,8 +190,12 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                         const __grid_constant__ CUtensorMap tmFlow, const float* __restrict__ f2,
                         const float* __restrict__ flow, float* __restrict__ out, float* __restrict__ warped_out,
                         int C, int H, int W, int tiles_x, int tiles_y, int ntiles, int act, float slope,
-                        long long obs)
+                        long long obs, long long fbs, const float* __restrict__ coarse,
+                        float* __restrict__ flow_out, long long fobs)
 {
+    // flow source: `flow` (image n's [2][H][W] block at flow + n*fbs; tmFlow maps it), or, when `coarse` is
+    // given ([B][2][H/2][W/2] dense; tmFlow maps THAT), flow = F.upsample(coarse, 2, 'bilinear') * 2
+    // (model.py:78) evaluated by the P warp, which also writes the tile's fine flow to flow_out + n*fobs.
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, HWD = Cfg::HWD;
     constexpr int WP = Cfg::WP, WW = Cfg::WW, WH = Cfg::WH, F1W = Cfg::F1W, F1H = Cfg::F1H;
@@ -273,8 +286,14 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
         prefetch_tmap(&tmFlow);
         auto request_flow = [&](int lt) {    // flow tile + halo of local tile lt -> sFlow[lt & 1]
             const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
-            mbar_expect_tx(&barFlow[lt & 1], Cfg::FLOW_BYTES);
-            tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 - R, tj.y0 - R, 0, tj.n);
+            if (coarse != nullptr) {         // the coarse box that covers the tile + halo
+                mbar_expect_tx(&barFlow[lt & 1], Cfg::CFLOW_BYTES);
+                tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 / 2 - Cfg::CW_OFF,
+                            tj.y0 / 2 - Cfg::CH_OFF, 0, tj.n);
+            } else {
+                mbar_expect_tx(&barFlow[lt & 1], Cfg::FLOW_BYTES);
+                tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 - R, tj.y0 - R, 0, tj.n);
+            }
         };
         if (my_tiles > 0) request_flow(0);
         if (my_tiles > 1) request_flow(1);
@@ -333,7 +352,25 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                     int meta = TAP_EMPTY;
                     if (y >= 0 && y < H && x >= 0 && x < W) {
-                        const float u = sfl[i], v = sfl[NHALO + i];
+                        float u, v;
+                        if (coarse != nullptr) {
+                            constexpr int CWB = Cfg::CWB, CPL = Cfg::CHB * Cfg::CWB;
+                            int xl, xr, yl, yr;
+                            const float lx1 = up2_source(x, W >> 1, xl, xr), ly1 = up2_source(y, H >> 1, yl, yr);
+                            const int cx0 = tc.x0 / 2 - Cfg::CW_OFF, cy0 = tc.y0 / 2 - Cfg::CH_OFF;
+                            const int ia = (yl - cy0) * CWB + (xl - cx0), ib = (yl - cy0) * CWB + (xr - cx0);
+                            const int ic = (yr - cy0) * CWB + (xl - cx0), id = (yr - cy0) * CWB + (xr - cx0);
+                            u = up2_blend(sfl[ia], sfl[ib], sfl[ic], sfl[id], lx1, ly1);
+                            v = up2_blend(sfl[CPL + ia], sfl[CPL + ib], sfl[CPL + ic], sfl[CPL + id], lx1, ly1);
+                            if (flow_out != nullptr && hy >= R && hy < R + TH && hx >= R && hx < R + TW) {
+                                float* fo = flow_out + (size_t)tc.n * (size_t)fobs + (size_t)y * W + x;
+                                fo[0] = u;
+                                fo[HW] = v;
+                            }
+                        } else {
+                            u = sfl[i];
+                            v = sfl[NHALO + i];
+                        }
                         if (fabsf(u) < 1.0e6f && fabsf(v) < 1.0e6f) {          // rejects NaN / Inf as well
                             // floor + fraction of the flow first: the fraction is exact in fp32 (pwc_common.cuh)
                             const float fu = floorf(u), fv = floorf(v);
@@ -436,7 +473,9 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
             }
             if (any_global) {
                 // outliers: recompute the tap from the flow and gather from global memory
-                const float* un = flow + (size_t)tc.n * 2 * HW;
+                const float* un = coarse ? nullptr : flow + (size_t)tc.n * (size_t)fbs;
+                const int Hc = H >> 1, Wc = W >> 1;
+                const float* cu = coarse ? coarse + (size_t)tc.n * 2 * Hc * Wc : nullptr;
 #pragma unroll
                 for (int j = 0; j < PXB; ++j) {
                     if (toff[j] == TAP_GLOBAL) {
@@ -444,7 +483,14 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                         int hy, hx;
                         halo_item<HWD>(i, hy, hx);
                         const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
-                        const Tap tp = make_tap(x, y, __ldg(un + (size_t)y * W + x), __ldg(un + HW + (size_t)y * W + x), H, W);
+                        float fu, fv;
+                        if (coarse != nullptr) {
+                            up2_flow_at(cu, cu + Hc * Wc, Hc, Wc, x, y, fu, fv);
+                        } else {
+                            fu = __ldg(un + (size_t)y * W + x);
+                            fv = __ldg(un + HW + (size_t)y * W + x);
+                        }
+                        const Tap tp = make_tap(x, y, fu, fv, H, W);
 #pragma unroll
                         for (int c = 0; c < CK; ++c)
                             v[j][c] = (c0 + c < C && tp.off >= 0)

@@ -241,6 +241,47 @@ def warp(x, flow):
     return WarpFunction.apply(x, flow)
 
 
+def _dense_image_view(t, shape, what):
+    """`t` must be a view of `shape` whose images are dense ([C,H,W] contiguous) -- only the batch stride is free."""
+    B, C, H, W = shape
+    if tuple(t.shape) != tuple(shape) or t.stride()[1:] != (H * W, W, 1) or (B > 1 and t.stride(0) < C * H * W):
+        raise ValueError(f"{what} must be a [{B},{C},{H},{W}] view with dense images, got shape "
+                         f"{tuple(t.shape)} strides {t.stride()}")
+    return int(t.stride(0)) if B > 1 else 0
+
+
+def warp_correlation_coarse_into(out, flow_out, x1, x2, coarse_flow, pad_size=4, kernel_size=1,
+                                 max_displacement=4, stride1=1, stride2=1, act=False, slope=0.01,
+                                 return_warped=False):
+    """model.py:78-84 in one launch (inference only): the flow arrives at the previous pyramid level's
+    resolution (`coarse_flow` [B,2,H/2,W/2]); the kernel evaluates `F.upsample(coarse_flow, 2, 'bilinear') * 2`
+    itself (bit for bit as torch does), writes that fine flow to the view `flow_out` ([B,2,H,W], dense images,
+    free batch stride) and the cost volume to the view `out` -- typically the last two channels and the middle
+    81 channels of the flow estimator's concatenated input (model.py:89-91)."""
+    dev = _check_inputs(x1, x2, coarse_flow, out, flow_out)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (x1, x2, coarse_flow)):
+        raise RuntimeError("warp_correlation_coarse_into is inference-only; under autograd keep the flow as a tensor "
+                           "(F.interpolate) and use warp_correlation")
+    if x1.shape != x2.shape or x1.dim() != 4:
+        raise ValueError("x1/x2 must be 4-D tensors of identical shape")
+    B, C, H, W = x1.shape
+    if H % 2 or W % 2 or tuple(coarse_flow.shape) != (B, 2, H // 2, W // 2):
+        raise ValueError(f"coarse_flow must be [B,2,H/2,W/2] = {(B, 2, H // 2, W // 2)}, got {tuple(coarse_flow.shape)}")
+    oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+    obs = _dense_image_view(out, (B, oc, oh, ow), "out")
+    fobs = _dense_image_view(flow_out, (B, 2, H, W), "flow_out")
+    x1, x2 = x1.detach().contiguous(), x2.detach().contiguous()
+    coarse_flow = coarse_flow.detach().contiguous()
+    warped = torch.empty_like(x2) if return_warped else None
+    with _on_device(dev):
+        ok = _lib.load().pwc_warpcorr_forward_coarse(
+            _ptr(x1), _ptr(x2), _ptr(coarse_flow), _ptr(out), obs, _ptr(flow_out), fobs, _ptr(warped),
+            B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+            int(bool(act)), float(slope), _stream())
+    _lib.check(ok, "pwc_warpcorr_forward_coarse")
+    return (out, warped) if return_warped else out
+
+
 def warp_correlation_into(out, x1, x2, flow, pad_size=4, kernel_size=1, max_displacement=4, stride1=1,
                           stride2=1, act=False, slope=0.01, return_warped=False):
     """Inference-only variant that writes the cost volume into `out`, a [B, D*D, oh, ow] *view* whose

@@ -121,6 +121,7 @@ class Net(nn.Module):
                 args.search_range, activation=bool(args.corr_activation), negative_slope=0.01, return_warped=True)
         self._own_ops = ops is None
         self._direct_concat = ops is None and args.search_range == 4 and not cost_volume_layer
+        self._fold_upsample = True      # SURVEY.md section 8 row f1 (inference; switched off by the parity tests)
         self.flow_estimators = []
         for l, ch in enumerate(args.lv_chs[::-1] + [3]):
             est = OpticalFlowEstimator(args, ch + (args.search_range * 2 + 1) ** 2 + 2)
@@ -147,6 +148,31 @@ class Net(nn.Module):
         flows, warps = [], []
         flow = None
         for l, (x1, x2) in enumerate(zip(pyr1, pyr2)):
+            if (l > 0 and self._direct_concat and self._fold_upsample and not torch.is_grad_enabled()
+                    and x1.dtype == torch.float32 and flow.dtype == torch.float32):
+                # inference: model.py:78-91 without the upsample / multiply / cat launches -- the kernel takes
+                # the previous level's flow, upsamples it itself (bit for bit F.interpolate(...) * 2) and writes
+                # both the fine flow and the cost volume into the estimator's input [x1 | corr | flow]
+                C = x1.size(1)
+                est_in = torch.empty((x1.size(0), C + 81 + 2, x1.size(2), x1.size(3)), dtype=x1.dtype, device=x1.device)
+                est_in[:, :C] = x1
+                _, x2_warp = self.warp_corr(x1, x2, None, out=est_in[:, C:C + 81], coarse_flow=flow,
+                                            flow_out=est_in[:, C + 81:])
+                flow = est_in[:, C + 81:]
+                flow_coarse = self.flow_estimators[l](est_in)
+                if args.residual:
+                    flow_coarse = flow_coarse + flow
+                if l == args.output_level:   # model.py:101-108
+                    scale = 2 ** (args.num_levels - args.output_level - 1)
+                    flow = F.interpolate(flow_coarse, scale_factor=scale, mode="bilinear", align_corners=False) * scale
+                    flow = flow + self.context_network(torch.cat([pyr1[-1], flow], dim=1))
+                    flows.append(flow)
+                    warps.append(x2_warp.detach())
+                    break
+                flow = flow_coarse
+                flows.append(flow)
+                warps.append(x2_warp.detach())
+                continue
             if l == 0:   # model.py:74-76: zero flow at the coarsest level (the warp is then the identity)
                 flow = torch.zeros((x1.size(0), 2, x1.size(2), x1.size(3)), dtype=x1.dtype, device=x1.device)
             else:        # model.py:78: F.upsample(..., 'bilinear') == align_corners=False

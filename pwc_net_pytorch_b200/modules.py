@@ -48,9 +48,18 @@ class FusedWarpCorrelation(nn.Module):
         return cls(pad_size=search_range * 2 + 1, kernel_size=1,
                    max_displacement=search_range * 2 + 1, stride1=1, stride2=2, **kw)
 
-    def forward(self, x1, x2, flow=None, out=None):
+    def forward(self, x1, x2, flow=None, out=None, coarse_flow=None, flow_out=None):
         """`out` (inference only): a [B, 81, H, W] view to write into, e.g. the channel slice of the flow
-        estimator's concatenated input; see functional.warp_correlation_into."""
+        estimator's concatenated input; see functional.warp_correlation_into.
+        `coarse_flow` + `flow_out` (inference only, with `out`): the flow at the previous pyramid level; the
+        kernel upsamples it itself (model.py:78) and writes the fine flow to `flow_out`; see
+        functional.warp_correlation_coarse_into."""
+        if coarse_flow is not None:
+            if out is None or flow_out is None or flow is not None:
+                raise ValueError("coarse_flow needs out= and flow_out= views and no flow=")
+            return PF.warp_correlation_coarse_into(out, flow_out, x1, x2, coarse_flow, self.pad_size, self.kernel_size,
+                                                   self.max_displacement, self.stride1, self.stride2,
+                                                   self.activation, self.negative_slope, self.return_warped)
         if out is not None:
             return PF.warp_correlation_into(out, x1, x2, flow, self.pad_size, self.kernel_size,
                                             self.max_displacement, self.stride1, self.stride2,
