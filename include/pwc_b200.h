@@ -141,6 +141,21 @@ int pwc_warpcorr_backward(const float *grad_out, const float *f1, const float *f
                           int stride1, int stride2,
                           int act, float slope, cudaStream_t stream);
 
+/* ---- same, reading the output gradient (and, for act != 0, the forward output) through a batch stride:
+ * image n's [D*D,H,W] block of grad_out starts at grad_out + n * grad_out_batch_stride floats, that of out
+ * at out + n * out_batch_stride (0 = dense).  This is how the gradient of the flow estimator's concatenated
+ * input [x1 | corr | flow] (model.py:89-91) is consumed in place, without a slice copy, when the forward
+ * wrote the cost volume there with pwc_warpcorr_forward_strided. ------------------------------------------ */
+int pwc_warpcorr_backward_strided(const float *grad_out, long long grad_out_batch_stride,
+                                  const float *f1, const float *f2, const float *flow,
+                                  const float *out, long long out_batch_stride, const float *warped,
+                                  float *grad_f1, float *grad_f2, float *grad_flow,
+                                  void *workspace, long long workspace_bytes,
+                                  int B, int C, int H, int W,
+                                  int pad_size, int kernel_size, int max_displacement,
+                                  int stride1, int stride2,
+                                  int act, float slope, cudaStream_t stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *pwc_last_error(void);          /* thread-local, never NULL */
 int pwc_abi_version(void);                 /* == PWC_B200_ABI_VERSION */

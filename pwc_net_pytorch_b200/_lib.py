@@ -31,6 +31,7 @@ EXPORTS = (
     "pwc_warpcorr_forward_coarse",
     "pwc_warpcorr_backward_workspace",
     "pwc_warpcorr_backward",
+    "pwc_warpcorr_backward_strided",
     "pwc_last_error",
     "pwc_abi_version",
     "pwc_launch_count",
@@ -71,6 +72,10 @@ def _declare(L):
     L.pwc_warpcorr_backward.argtypes = ([_c_float_p] * 9 + [ctypes.c_void_p, ctypes.c_longlong] +
                                         [_int] * 9 + [_int, ctypes.c_float] + [_stream])
     L.pwc_warpcorr_backward.restype = _int
+    L.pwc_warpcorr_backward_strided.argtypes = ([_c_float_p, ctypes.c_longlong] + [_c_float_p] * 4 + [ctypes.c_longlong] +
+                                                [_c_float_p] * 4 + [ctypes.c_void_p, ctypes.c_longlong] +
+                                                [_int] * 9 + [_int, ctypes.c_float] + [_stream])
+    L.pwc_warpcorr_backward_strided.restype = _int
     L.pwc_last_error.argtypes = []
     L.pwc_last_error.restype = ctypes.c_char_p
     L.pwc_abi_version.argtypes = []

@@ -31,7 +31,8 @@ template <class Cfg, int SIGN>
 __global__ void __launch_bounds__(Cfg::NT)
 corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
                 const float* __restrict__ X, float* __restrict__ res,
-                int C, int H, int W, int tiles_x, int tiles_y, int cgroup, float slope)
+                int C, int H, int W, int tiles_x, int tiles_y, int cgroup, float slope, long long gbs,
+                long long gate_bs)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, r = Cfg::r, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, NT = Cfg::NT, HH = Cfg::HH, HP = Cfg::HP;
@@ -46,8 +47,8 @@ corr_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
     const int y = y0t + ly, x = x0t + lx;
     const bool inside = (y < H) && (x < W);
     const size_t HW = (size_t)H * W;
-    const float* gon = gout + (size_t)n * (D * D) * HW;
-    const float* gaten = gate ? gate + (size_t)n * (D * D) * HW : nullptr;
+    const float* gon = gout + (size_t)n * (size_t)gbs;          // batch strides of the output gradient / the gate
+    const float* gaten = gate ? gate + (size_t)n * (size_t)gate_bs : nullptr;
     const float* Xn = X + (size_t)n * C * HW;
     float* resn = res + (size_t)n * C * HW;
 

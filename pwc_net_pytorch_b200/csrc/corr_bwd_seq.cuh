@@ -49,7 +49,7 @@ template <int SIGN>
 __global__ void __launch_bounds__(BwdSeqCfg::NT, 1)
 corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                     const float* __restrict__ gout, float* __restrict__ res,
-                    int C, int H, int W, int tiles_x, int tiles_y, int nitems, int nsc)
+                    int C, int H, int W, int tiles_x, int tiles_y, int nitems, int nsc, long long gbs)
 {
     using Cfg = BwdSeqCfg;
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R, CPI = Cfg::CPI;
@@ -89,7 +89,7 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const TileCoord tc = tile_coord(item / nsc, tiles_x, tiles_y, TH, TW);
-            const float* gon = gout + (size_t)tc.n * (D * D) * HW;
+            const float* gon = gout + (size_t)tc.n * (size_t)gbs;      // gbs: batch stride of the output gradient
             for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32) {
                 const int j = it * D + dyi, slot = j % NTS;
                 if (j >= NTS) mbar_wait(&barTapFree[slot], ((j / NTS) - 1) & 1);

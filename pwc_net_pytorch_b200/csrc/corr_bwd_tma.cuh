@@ -143,7 +143,7 @@ template <class Cfg, int SIGN>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                     const float* __restrict__ gout, float* __restrict__ res,
-                    int C, int H, int W, int tiles_x, int tiles_y, int ntiles)
+                    int C, int H, int W, int tiles_x, int tiles_y, int ntiles, long long gbs)
 {
     constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;
     constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, WP = Cfg::WP, PP = Cfg::PP;
@@ -189,7 +189,7 @@ corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int lt = 0; lt < my_tiles; ++lt) {
             const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
             if (lt >= 1) mbar_wait(barTapFree, (lt - 1) & 1);      // tile lt-1's taps are in the consumers' registers
-            const float* gon = gout + (size_t)tc.n * (D * D) * HW;
+            const float* gon = gout + (size_t)tc.n * (size_t)gbs;      // gbs: batch stride of the output gradient
             for (int dyi = sw; dyi < D; dyi += Cfg::NSTAGE / 32)
                 stage_tap_row<S2, SIGN>(sTap + dyi * D * (TH * TW), gon, dyi, tc, H, W, HW, lane, gout);
             cp_async_mbar_arrive(barTap);       // arrives once this thread's asynchronous copies have landed

@@ -100,7 +100,8 @@ flow_up2_kernel(const float* __restrict__ coarse, float* __restrict__ fine, long
 __global__ void __launch_bounds__(256)
 corr_bwd_generic_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
                         const float* __restrict__ f1, const float* __restrict__ second,
-                        float* __restrict__ g1, float* __restrict__ g2, CorrGeom g, float slope)
+                        float* __restrict__ g1, float* __restrict__ g2, CorrGeom g, float slope, long long gbs,
+                        long long gate_bs)
 {
     const size_t total = (size_t)g.B * g.C * g.H * g.W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,8 +114,8 @@ corr_bwd_generic_kernel(const float* __restrict__ gout, const float* __restrict_
     const float* f1n = f1 + (size_t)n * g.C * HW;
     const float* f2n = second + (size_t)n * g.C * HW;
     const size_t ohw = (size_t)g.oh * g.ow;
-    const float* gon = gout + (size_t)n * g.oc * ohw;
-    const float* gaten = gate ? gate + (size_t)n * g.oc * ohw : nullptr;
+    const float* gon = gout + (size_t)n * (size_t)gbs;           // batch strides of the output gradient / the gate
+    const float* gaten = gate ? gate + (size_t)n * (size_t)gate_bs : nullptr;
     const int y = yy * g.s1 + g.pad, x = xx * g.s1 + g.pad;
     const float nelems = (float)(g.k * g.k * g.C);
 
@@ -397,12 +398,14 @@ zero2_kernel(float4* __restrict__ a, size_t na4, float4* __restrict__ b, size_t 
 // be gated on the way.  n4 = number of float4 elements.
 __global__ void __launch_bounds__(256)
 gate_grad_kernel(const float4* __restrict__ gout, const float4* __restrict__ out, float4* __restrict__ dst,
-                 size_t n4, float slope)
+                 size_t n4, float slope, size_t per_image4, size_t gbs4, size_t obs4)
 {
+    // dst is dense; gout / out may carry a batch stride (per_image4, gbs4, obs4 in float4 units)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    float4 g = __ldg(gout + i);
-    const float4 o = __ldg(out + i);
+    const size_t n = i / per_image4, r = i - n * per_image4;
+    float4 g = __ldg(gout + n * gbs4 + r);
+    const float4 o = __ldg(out + n * obs4 + r);
     if (o.x < 0.0f) g.x *= slope;
     if (o.y < 0.0f) g.y *= slope;
     if (o.z < 0.0f) g.z *= slope;

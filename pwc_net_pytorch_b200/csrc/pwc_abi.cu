@@ -195,11 +195,12 @@ int launch_fwd_small(const float* f1, const float* f2, const FlowSpec& fs, float
 
 template <int S2, bool HAS_FLOW>
 int launch_bwd_small(const float* gout, const float* gate, const float* f1, const float* f2, const float* flow,
-                     float* gf1, float* gf2, float* gflow, const pwc::CorrGeom& g, float slope, cudaStream_t st)
+                     float* gf1, float* gf2, float* gflow, const pwc::CorrGeom& g, float slope, long long gbs,
+                     long long gate_bs, cudaStream_t st)
 {
     const pwc::SmallPlan p = small_plan_for(g, HAS_FLOW, true);
     return launch_small(pwc::warpcorr_bwd_small_kernel<S2, HAS_FLOW>, "warpcorr_bwd_small_kernel", p.smem, g.B, p.ks, st, gout, gate, f1, f2, flow, gf1, gf2,
-                        gflow, g.C, g.H, g.W, p.cs, p.csp, slope);
+                        gflow, g.C, g.H, g.W, p.cs, p.csp, slope, gbs, gate_bs);
 }
 
 
@@ -396,7 +397,7 @@ int forward_impl(const float* f1, const float* f2, FlowSpec fs, float* out, floa
 
 template <int S2, int SIGN, int TW = 32, int TH = 8>
 int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, float* res,
-                         const pwc::CorrGeom& g, float slope, cudaStream_t st)
+                         const pwc::CorrGeom& g, float slope, long long gbs, long long gate_bs, cudaStream_t st)
 {
     using Cfg = pwc::BwdCfg<9, S2, 16, TW, TH>;
     auto kern = pwc::corr_bwd_kernel<Cfg, SIGN>;
@@ -416,20 +417,20 @@ int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, f
     int cgroup = g.C;
     while (cgroup > Cfg::CK && blocks * pwc::cdiv(g.C, cgroup) < 296) cgroup = pwc::round_up(pwc::cdiv(cgroup, 2), Cfg::CK);
     const dim3 grid((unsigned)blocks, (unsigned)pwc::cdiv(g.C, cgroup));
-    kern<<<grid, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, cgroup, slope);
+    kern<<<grid, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, cgroup, slope, gbs, gate_bs);
     return check_launch("corr_bwd_kernel");
 }
 
 // returns 1 ok, 0 error, -1 "not taken" (caller falls back to the plain tiled kernel)
 template <int S2, int CK, int SIGN>
-int launch_bwd_tma(const float* gout, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
+int launch_bwd_tma(const float* gout, long long gbs, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
 {
     using Cfg = pwc::BwdTmaCfg<S2, CK>;
     CUtensorMap mX, mG;
     if (!make_nchw_map(&mX, X, g.B, g.C, g.H, g.W, Cfg::WP, Cfg::HH, CK)) return -1;
     // output-gradient prefetch box: the tile (g1) or the tile + halo (gradient w.r.t. the second operand)
     if (!make_nchw_map(&mG, gout, g.B, 81, g.H, g.W, SIGN > 0 ? Cfg::TW : Cfg::HWD, SIGN > 0 ? Cfg::TH : Cfg::HH,
-                       Cfg::GBOX_C))
+                       Cfg::GBOX_C, gbs))
         return -1;
     auto kern = pwc::corr_bwd_tma_kernel<Cfg, SIGN>;
     const size_t smem = Cfg::smem_bytes();
@@ -448,19 +449,19 @@ int launch_bwd_tma(const float* gout, const float* X, float* res, const pwc::Cor
     if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         sm_count = 148;
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
-    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, gbs);
     return check_launch("corr_bwd_tma_kernel");
 }
 
 // stride2 == 1: threads own complete outputs (corr_bwd_seq.cuh).  returns 1 ok, 0 error, -1 "not taken"
 template <int SIGN>
-int launch_bwd_seq(const float* gout, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
+int launch_bwd_seq(const float* gout, long long gbs, const float* X, float* res, const pwc::CorrGeom& g, cudaStream_t st)
 {
     using Cfg = pwc::BwdSeqCfg;
     CUtensorMap mX, mG;
     if (!make_nchw_map(&mX, X, g.B, g.C, g.H, g.W, Cfg::WP, Cfg::HH, Cfg::CPI)) return -1;
     if (!make_nchw_map(&mG, gout, g.B, 81, g.H, g.W, SIGN > 0 ? Cfg::TW : Cfg::HWD, SIGN > 0 ? Cfg::TH : Cfg::HH,
-                       Cfg::GBOX_C))
+                       Cfg::GBOX_C, gbs))
         return -1;
     auto kern = pwc::corr_bwd_seq_kernel<SIGN>;
     const size_t smem = Cfg::smem_bytes();
@@ -478,17 +479,17 @@ int launch_bwd_seq(const float* gout, const float* X, float* res, const pwc::Cor
     if (nitems > 0x3fffffffLL) return fail("grid too large");
     const int sms = sm_count_of_current_device();
     const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
-    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)nitems, nsc);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)nitems, nsc, gbs);
     return check_launch("corr_bwd_seq_kernel");
 }
 
 template <int S2, int SIGN>
 int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float* res,
-                     const pwc::CorrGeom& g, float slope, cudaStream_t st)
+                     const pwc::CorrGeom& g, float slope, long long gbs, long long gate_bs, cudaStream_t st)
 {
-    if (g.W <= 8 && g.H <= 8) return launch_bwd_tiled_cfg<S2, SIGN, 8, 8>(gout, gate, X, res, g, slope, st);
-    if (g.W <= 16) return launch_bwd_tiled_cfg<S2, SIGN, 16, 16>(gout, gate, X, res, g, slope, st);
-    return launch_bwd_tiled_cfg<S2, SIGN, 32, 8>(gout, gate, X, res, g, slope, st);
+    if (g.W <= 8 && g.H <= 8) return launch_bwd_tiled_cfg<S2, SIGN, 8, 8>(gout, gate, X, res, g, slope, gbs, gate_bs, st);
+    if (g.W <= 16) return launch_bwd_tiled_cfg<S2, SIGN, 16, 16>(gout, gate, X, res, g, slope, gbs, gate_bs, st);
+    return launch_bwd_tiled_cfg<S2, SIGN, 32, 8>(gout, gate, X, res, g, slope, gbs, gate_bs, st);
 }
 
 // g1 (w.r.t. f1) and g2 (w.r.t. the second operand as given, i.e. the warped features).
@@ -496,57 +497,72 @@ int launch_bwd_tiled(const float* gout, const float* gate, const float* X, float
 // gated_scratch (optional, B*81*H*W floats, 16-byte aligned): room for the LeakyReLU-gated output
 // gradient; without it a gated backward stays on the plain tiled kernels.  *gated_done tells a caller
 // that splits the two gradients over two calls that the scratch already holds the gated gradient.
+// Strides of the backward's strided inputs: gbs = floats between consecutive images of grad_out, gate_bs = the
+// same for the forward output that gates it (act); 0 = dense.  This is how the gradient of the flow estimator's
+// concatenated input [x1 | corr | flow] (model.py:89-91) is consumed in place: grad_out = grad_in + C*H*W with
+// batch stride (C + 83)*H*W, no slice copy.
+struct GradStrides { long long gbs, gate_bs; };
+
 int corr_backward_impl(const float* gout, const float* gate, const float* f1, const float* second,
                        float* g1, float* g2, const pwc::CorrGeom& g, float slope, cudaStream_t st, int which = 3,
-                       float* gated_scratch = nullptr, bool* gated_done = nullptr)
+                       float* gated_scratch = nullptr, bool* gated_done = nullptr, GradStrides gs = {0, 0})
 {
     if (g.s1 != 1)
         return fail("correlation backward requires stride1 == 1 (got %d): the reference kernels "
                     "address gradInput out of range otherwise", g.s1);
+    const long long dense = (long long)g.oc * g.oh * g.ow;
+    long long gbs = gs.gbs ? gs.gbs : dense, gate_bs = gs.gate_bs ? gs.gate_bs : dense;
+    if (gbs < dense || gate_bs < dense) return fail("grad_out / out batch stride smaller than one image (%lld)", dense);
     if (which == 3 && small_plan_for(g, false, true).ok)
-        return g.s2 == 1 ? launch_bwd_small<1, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st)
-                         : launch_bwd_small<2, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, st);
+        return g.s2 == 1 ? launch_bwd_small<1, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, gbs, gate_bs, st)
+                         : launch_bwd_small<2, false>(gout, gate, f1, second, nullptr, g1, g2, nullptr, g, slope, gbs, gate_bs, st);
     if (fast_path(g)) {
         const float* any_in = second ? second : f1;
         float* any_out = g1 ? g1 : g2;
-        const bool gate_ok = !gate || (gated_scratch && (((uintptr_t)gate | (uintptr_t)gated_scratch) & 15) == 0);
-        if (gate_ok && tma_eligible(f1, any_in, any_out, g) && (((uintptr_t)g2 | (uintptr_t)g1 | (uintptr_t)gout) & 15) == 0) {
+        const bool gate_ok = !gate || (gated_scratch && (((uintptr_t)gate | (uintptr_t)gated_scratch) & 15) == 0 &&
+                                       (gate_bs & 3) == 0);
+        if (gate_ok && (gbs & 3) == 0 && tma_eligible(f1, any_in, any_out, g) &&
+            (((uintptr_t)g2 | (uintptr_t)g1 | (uintptr_t)gout) & 15) == 0) {
             const float* go = gout;
-            if (gate) {      // LeakyReLU backward as its own pass (the TMA kernels stage raw taps)
+            long long go_bs = gbs;
+            if (gate) {      // LeakyReLU backward as its own pass (the TMA kernels stage raw taps); dense result
                 if (!gated_done || !*gated_done) {
-                    const size_t n4 = (size_t)g.B * g.oc * g.H * g.W / 4;      // W % 4 == 0 on this path
+                    const size_t per4 = (size_t)dense / 4;                     // W % 4 == 0 on this path
+                    const size_t n4 = (size_t)g.B * per4;
                     pwc::gate_grad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
                         reinterpret_cast<const float4*>(gout), reinterpret_cast<const float4*>(gate),
-                        reinterpret_cast<float4*>(gated_scratch), n4, slope);
+                        reinterpret_cast<float4*>(gated_scratch), n4, slope, per4, (size_t)gbs / 4, (size_t)gate_bs / 4);
                     if (!check_launch("gate_grad_kernel")) return 0;
                     if (gated_done) *gated_done = true;
                 }
                 go = gated_scratch;
+                go_bs = dense;
             }
             int r1 = 1, r2 = 1;
             if (g.s2 == 1 && !g_disable_seq.load()) {
                 // threads own complete outputs (corr_bwd_seq.cuh): 90 / 100 us vs 111 / 108 us for the
                 // slice/reduce kernel at the level-2 shape
-                if (which & 1) r1 = launch_bwd_seq<+1>(go, second, g1, g, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_seq<-1>(go, f1, g2, g, st);
+                if (which & 1) r1 = launch_bwd_seq<+1>(go, go_bs, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_seq<-1>(go, go_bs, f1, g2, g, st);
             } else if (g.s2 == 1) {
-                if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(go, second, g1, g, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, f1, g2, g, st);
+                if (which & 1) r1 = launch_bwd_tma<1, 4, +1>(go, go_bs, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<1, 4, -1>(go, go_bs, f1, g2, g, st);
             } else {
-                if (which & 1) r1 = launch_bwd_tma<2, 2, +1>(go, second, g1, g, st);
-                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<2, 2, -1>(go, f1, g2, g, st);
+                if (which & 1) r1 = launch_bwd_tma<2, 2, +1>(go, go_bs, second, g1, g, st);
+                if ((which & 2) && r1 > 0) r2 = launch_bwd_tma<2, 2, -1>(go, go_bs, f1, g2, g, st);
             }
             if (r1 == 0 || r2 == 0) return 0;
             if (r1 > 0 && r2 > 0) return 1;
         }
         if (g.s2 == 1)
-            return (!(which & 1) || launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, st)) &&
-                   (!(which & 2) || launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, st));
-        return (!(which & 1) || launch_bwd_tiled<2, +1>(gout, gate, second, g1, g, slope, st)) &&
-               (!(which & 2) || launch_bwd_tiled<2, -1>(gout, gate, f1, g2, g, slope, st));
+            return (!(which & 1) || launch_bwd_tiled<1, +1>(gout, gate, second, g1, g, slope, gbs, gate_bs, st)) &&
+                   (!(which & 2) || launch_bwd_tiled<1, -1>(gout, gate, f1, g2, g, slope, gbs, gate_bs, st));
+        return (!(which & 1) || launch_bwd_tiled<2, +1>(gout, gate, second, g1, g, slope, gbs, gate_bs, st)) &&
+               (!(which & 2) || launch_bwd_tiled<2, -1>(gout, gate, f1, g2, g, slope, gbs, gate_bs, st));
     }
     const size_t total = (size_t)g.B * g.C * g.H * g.W;
-    pwc::corr_bwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gout, gate, f1, second, g1, g2, g, slope);
+    pwc::corr_bwd_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gout, gate, f1, second, g1, g2, g, slope,
+                                                                                 gbs, gate_bs);
     return check_launch("corr_bwd_generic_kernel");
 }
 
@@ -748,7 +764,7 @@ long long pwc_warpcorr_backward_workspace(int B, int C, int H, int W, int has_fl
     return (long long)sizeof(float) * (2LL * B * C * H * W + 8LL * B * ((C + 7) / 8) * H * W + 81LL * B * H * W);
 }
 
-int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
+static int warpcorr_backward_impl(const float* grad_out, GradStrides gs, const float* f1, const float* f2,
                           const float* flow, const float* out, const float* warped_in, float* grad_f1, float* grad_f2,
                           float* grad_flow, void* workspace, long long workspace_bytes, int B,
                           int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
@@ -759,11 +775,13 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     pwc::CorrGeom g;
     if (!make_geom(g, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2)) return 0;
     const float* gate = act ? out : nullptr;
-    if (!flow) return corr_backward_impl(grad_out, gate, f1, f2, grad_f1, grad_f2, g, slope, stream);
+    const long long dense = (long long)g.oc * g.oh * g.ow;
+    const long long gbs = gs.gbs ? gs.gbs : dense, gate_bs = gs.gate_bs ? gs.gate_bs : dense;
+    if (!flow) return corr_backward_impl(grad_out, gate, f1, f2, grad_f1, grad_f2, g, slope, stream, 3, nullptr, nullptr, gs);
     if (!grad_flow) return fail("pwc_warpcorr_backward: grad_flow is required when flow is given");
     if (small_plan_for(g, true, true).ok)      // coarse levels: the whole backward is one launch, no workspace
-        return g.s2 == 1 ? launch_bwd_small<1, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream)
-                         : launch_bwd_small<2, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, stream);
+        return g.s2 == 1 ? launch_bwd_small<1, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, gbs, gate_bs, stream)
+                         : launch_bwd_small<2, true>(grad_out, gate, f1, f2, flow, grad_f1, grad_f2, grad_flow, g, slope, gbs, gate_bs, stream);
     const long long need = pwc_warpcorr_backward_workspace(B, C, H, W, 1, pad_size, kernel_size,
                                                            max_displacement, stride1, stride2);
     if (!workspace || workspace_bytes < need)
@@ -779,7 +797,7 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
     const bool split_ok = fast_path(g);      // the tiled kernels compute the two gradients in separate launches
     if (vec_ok && split_ok) {
         // 1. gradient w.r.t. the warped features (needs f1 and grad_out only)
-        if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2, gated, &gated_done)) return 0;
+        if (!corr_backward_impl(grad_out, gate, f1, nullptr, nullptr, gwarped, g, slope, stream, 2, gated, &gated_done, gs)) return 0;
         // 2. zero the scatter scratch: independent of step 1, launched into its tail
         if (!scatter_zero(scratch, grad_flow, B, C, H, W, stream)) return 0;
         // 3. scatter to the scratch + flow gradient; the same pass re-materialises x2_warp when the forward did
@@ -787,7 +805,7 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
         if (!scatter_accumulate(gwarped, f2, flow, grad_flow, scratch, warped_in ? nullptr : wbuf, B, C, H, W, stream))
             return 0;
         // 4. gradient w.r.t. f1 (needs x2_warp, does not touch the scratch)
-        if (!corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1, gated, &gated_done))
+        if (!corr_backward_impl(grad_out, gate, f1, warped_in ? warped_in : wbuf, grad_f1, nullptr, g, slope, stream, 1, gated, &gated_done, gs))
             return 0;
         // 5. scratch -> grad_f2 (NCHW): independent of step 4, launched into its tail
         return scatter_finish(scratch, grad_f2, B, C, H, W, true, stream);
@@ -797,9 +815,32 @@ int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f
         if (!pwc_warp_forward(f2, flow, wbuf, B, C, H, W, stream)) return 0;
         warped = wbuf;
     }
-    if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream, 3, gated, &gated_done)) return 0;
+    if (!corr_backward_impl(grad_out, gate, f1, warped, grad_f1, gwarped, g, slope, stream, 3, gated, &gated_done, gs)) return 0;
     if (vec_ok) return warp_backward_scratch(gwarped, f2, flow, grad_f2, grad_flow, scratch, nullptr, B, C, H, W, stream);
     return pwc_warp_backward(gwarped, f2, flow, grad_f2, grad_flow, B, C, H, W, stream);
+}
+
+int pwc_warpcorr_backward(const float* grad_out, const float* f1, const float* f2,
+                          const float* flow, const float* out, const float* warped_in, float* grad_f1, float* grad_f2,
+                          float* grad_flow, void* workspace, long long workspace_bytes, int B,
+                          int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
+                          int stride1, int stride2, int act, float slope, cudaStream_t stream)
+{
+    return warpcorr_backward_impl(grad_out, GradStrides{0, 0}, f1, f2, flow, out, warped_in, grad_f1, grad_f2, grad_flow,
+                                  workspace, workspace_bytes, B, C, H, W, pad_size, kernel_size, max_displacement, stride1,
+                                  stride2, act, slope, stream);
+}
+
+int pwc_warpcorr_backward_strided(const float* grad_out, long long grad_out_batch_stride, const float* f1,
+                                  const float* f2, const float* flow, const float* out, long long out_batch_stride,
+                                  const float* warped_in, float* grad_f1, float* grad_f2, float* grad_flow,
+                                  void* workspace, long long workspace_bytes, int B, int C, int H, int W,
+                                  int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                                  int act, float slope, cudaStream_t stream)
+{
+    return warpcorr_backward_impl(grad_out, GradStrides{grad_out_batch_stride, out_batch_stride}, f1, f2, flow, out,
+                                  warped_in, grad_f1, grad_f2, grad_flow, workspace, workspace_bytes, B, C, H, W, pad_size,
+                                  kernel_size, max_displacement, stride1, stride2, act, slope, stream);
 }
 
 int Correlation_forward_cuda_kernel(float* output, int ob, int oc, int oh, int ow, int, int, int,

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(SMALL_NT)
 warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restrict__ gate,
                           const float* __restrict__ f1, const float* __restrict__ f2,
                           const float* __restrict__ flow, float* __restrict__ gf1, float* __restrict__ gf2,
-                          float* __restrict__ gflow, int C, int H, int W, int cs, int csp, float slope)
+                          float* __restrict__ gflow, int C, int H, int W, int cs, int csp, float slope,
+                          long long gbs, long long gate_bs)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -272,8 +273,8 @@ warpcorr_bwd_small_kernel(const float* __restrict__ gout, const float* __restric
 
     // ---- stage: gated output gradient, f1 slice, taps; zero the accumulators ----
     {
-        const float* gon = gout + (size_t)n * (D * D) * HW;
-        const float* gaten = gate ? gate + (size_t)n * (D * D) * HW : nullptr;
+        const float* gon = gout + (size_t)n * (size_t)gbs;       // batch strides of the output gradient / the gate
+        const float* gaten = gate ? gate + (size_t)n * (size_t)gate_bs : nullptr;
         for (int i = tid; i < D * D * HW; i += NT) {
             float g = __ldg(gon + i);
             if (gaten && __ldg(gaten + i) < 0.0f) g *= slope;

@@ -231,6 +231,87 @@ class WarpCorrelationFunction(Function):
         return (g1, g2, gflow) + (None,) * 8
 
 
+class WarpCorrelationConcatFunction(Function):
+    """est_in = cat([x1, [leaky_relu](Correlation(x1, warp(x2, flow))), flow], 1) -- the flow estimator's
+    input (model.py:80-91) -- with the cost volume written by the kernel straight into its channel slice and,
+    in the backward, the gradient of that slice read in place (pwc_warpcorr_forward_strided /
+    pwc_warpcorr_backward_strided): no torch.cat copy of the 81 channels, no slice copy of their gradient.
+    Returns (est_in, x2_warp or None); flow may be None only together with a `flow_fill` tensor that supplies
+    the last two channels (level 0: zero flow, no warp)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, flow, flow_fill, pad_size, kernel_size, max_displacement, stride1, stride2,
+                act, slope, want_warped):
+        dev = _check_inputs(x1, x2, flow, flow_fill)
+        if x1.shape != x2.shape or x1.dim() != 4:
+            raise ValueError("x1/x2 must be 4-D tensors of identical shape")
+        B, C, H, W = x1.shape
+        tail = flow if flow is not None else flow_fill
+        if tail is None or tuple(tail.shape) != (B, 2, H, W):
+            raise ValueError(f"flow (or flow_fill) must be [B,2,H,W] = {(B, 2, H, W)}")
+        oc, oh, ow = corr_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+        if (oh, ow) != (H, W):
+            raise ValueError("the concatenated form needs an output of the input's size (pad == max_displacement + (k-1)/2, stride1 == 1)")
+        x1 = x1.contiguous()
+        x2 = x2.contiguous()
+        flow = None if flow is None else flow.contiguous()
+        est_in = torch.empty((B, C + oc + 2, H, W), dtype=torch.float32, device=dev)
+        est_in[:, :C].copy_(x1)
+        est_in[:, C + oc:].copy_(tail)
+        warped = torch.empty_like(x2) if want_warped else None
+        with _on_device(dev):
+            ok = _lib.load().pwc_warpcorr_forward_strided(
+                _ptr(x1), _ptr(x2), _ptr(flow), ctypes.c_void_p(est_in.data_ptr() + 4 * C * H * W),
+                (C + oc + 2) * H * W, _ptr(warped), B, C, H, W, pad_size, kernel_size, max_displacement, stride1,
+                stride2, int(bool(act)), float(slope), _stream())
+        _lib.check(ok, "pwc_warpcorr_forward_strided")
+        ctx.params = (pad_size, kernel_size, max_displacement, stride1, stride2, bool(act), float(slope), oc)
+        ctx.has_flow = flow is not None
+        keep_warp = want_warped and flow is not None
+        # est_in is saved only for the sign gate of the activation (its corr slice is the forward output)
+        ctx.save_for_backward(x1, x2, flow, est_in if act else None, warped if keep_warp else None)
+        if want_warped:
+            ctx.mark_non_differentiable(warped)
+            return est_in, warped
+        return est_in
+
+    @staticmethod
+    def backward(ctx, grad_est, *unused):
+        pad_size, kernel_size, max_displacement, stride1, stride2, act, slope, oc = ctx.params
+        x1, x2, flow, est_in, warped = ctx.saved_tensors
+        grad_est = grad_est.contiguous()
+        _check_inputs(grad_est)
+        B, C, H, W = x1.shape
+        per = (C + oc + 2) * H * W
+        g1 = torch.empty_like(x1)
+        g2 = torch.empty_like(x2)
+        gflow = torch.empty_like(flow) if flow is not None else None
+        L = _lib.load()
+        ws_bytes = int(L.pwc_warpcorr_backward_workspace(B, C, H, W, int(flow is not None), pad_size,
+                                                         kernel_size, max_displacement, stride1, stride2))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x1.device) if ws_bytes else None
+        off = 4 * C * H * W
+        with _on_device(x1.device):
+            ok = L.pwc_warpcorr_backward_strided(
+                ctypes.c_void_p(grad_est.data_ptr() + off), per, _ptr(x1), _ptr(x2), _ptr(flow),
+                None if est_in is None else ctypes.c_void_p(est_in.data_ptr() + off), per, _ptr(warped),
+                _ptr(g1), _ptr(g2), _ptr(gflow), _ptr(ws), ws_bytes, B, C, H, W,
+                pad_size, kernel_size, max_displacement, stride1, stride2, int(act), float(slope), _stream())
+        _lib.check(ok, "pwc_warpcorr_backward_strided")
+        g1 += grad_est[:, :C]                    # x1 is also the first C channels of est_in
+        gtail = grad_est[:, C + oc:]
+        if flow is not None:
+            gflow += gtail
+            return (g1, g2, gflow, None) + (None,) * 8
+        return (g1, g2, None, gtail.contiguous() if ctx.needs_input_grad[3] else None) + (None,) * 8
+
+
+def warp_correlation_concat(x1, x2, flow, flow_fill=None, pad_size=4, kernel_size=1, max_displacement=4, stride1=1,
+                            stride2=1, act=False, slope=0.01, return_warped=False):
+    return WarpCorrelationConcatFunction.apply(x1, x2, flow, flow_fill, pad_size, kernel_size, max_displacement,
+                                               stride1, stride2, act, slope, return_warped)
+
+
 def correlation(input1, input2, pad_size=3, kernel_size=3, max_displacement=20, stride1=1,
                 stride2=2, corr_multiply=1):
     return CorrelationFunction.apply(input1, input2, pad_size, kernel_size, max_displacement,

@@ -193,6 +193,10 @@ class Net(nn.Module):
                 est_in[:, :C] = x1
                 est_in[:, C + 81:] = flow
                 _, x2_warp = self.warp_corr(x1, x2, wflow, out=est_in[:, C:C + 81])
+            elif self._direct_concat:
+                # training: same buffer, recorded by autograd (the backward reads the gradient of the corr
+                # slice in place) -- no torch.cat copy and no slice copy of the 81 channels
+                est_in, x2_warp = self.warp_corr(x1, x2, wflow, concat=flow)
             else:
                 corr, x2_warp = self.warp_corr(x1, x2, wflow)
                 est_in = torch.cat([x1, corr, flow], dim=1)

@@ -48,12 +48,18 @@ class FusedWarpCorrelation(nn.Module):
         return cls(pad_size=search_range * 2 + 1, kernel_size=1,
                    max_displacement=search_range * 2 + 1, stride1=1, stride2=2, **kw)
 
-    def forward(self, x1, x2, flow=None, out=None, coarse_flow=None, flow_out=None):
+    def forward(self, x1, x2, flow=None, out=None, coarse_flow=None, flow_out=None, concat=None):
         """`out` (inference only): a [B, 81, H, W] view to write into, e.g. the channel slice of the flow
         estimator's concatenated input; see functional.warp_correlation_into.
         `coarse_flow` + `flow_out` (inference only, with `out`): the flow at the previous pyramid level; the
         kernel upsamples it itself (model.py:78) and writes the fine flow to `flow_out`; see
         functional.warp_correlation_coarse_into."""
+        if concat is not None:
+            # training path of model.py:89-91: returns (cat([x1, corr, flow]), x2_warp); `concat` is the tensor
+            # that fills the last two channels (the flow itself, or the zero flow of level 0 when flow is None)
+            return PF.warp_correlation_concat(x1, x2, flow, concat if flow is None else None, self.pad_size,
+                                              self.kernel_size, self.max_displacement, self.stride1, self.stride2,
+                                              self.activation, self.negative_slope, self.return_warped)
         if coarse_flow is not None:
             if out is None or flow_out is None or flow is not None:
                 raise ValueError("coarse_flow needs out= and flow_out= views and no flow=")

@@ -355,3 +355,72 @@ def test_net_with_folded_upsample_equals_unfolded_and_graphed():
         out_g, _ = graphed(x)
         for a, b in zip(out_g, plain):
             assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------
+# training-path write into the estimator's concat buffer (model.py:89-91) + strided output gradient
+# ---------------------------------------------------------------------------------------------------
+CONCAT_CASES = [((2, 32, 48, 56), CANON_CFG), ((2, 20, 40, 44), REF_CFG), ((3, 40, 12, 14), REF_CFG),
+                ((2, 196, 6, 7), CANON_CFG), ((1, 7, 18, 22), CANON_CFG), ((1, 5, 8, 12), (5, 3, 4, 1, 2)),
+                ((2, 32, 96, 112), REF_CFG)]
+
+
+@pytest.mark.parametrize("shape,cfg", CONCAT_CASES)
+@pytest.mark.parametrize("act", [False, True])
+@pytest.mark.parametrize("with_flow", [True, False])
+def test_concat_function_equals_cat_of_the_plain_op(shape, cfg, act, with_flow):
+    """warp_correlation_concat == torch.cat([x1, warp_correlation(...), flow], 1), values and every gradient
+    (the backward reads grad[:, C:C+81] through the batch stride: pwc_warpcorr_backward_strided)."""
+    from pwc_net_pytorch_b200 import functional as PF
+    B, C, H, W = shape
+    f1, f2, flow, rng = make_inputs(B, C, H, W, seed=113)
+    D2 = (2 * (cfg[2] // cfg[4]) + 1) ** 2
+    go = rng.standard_normal((B, C + D2 + 2, H, W)).astype(np.float32)
+    res = []
+    for concat in (True, False):
+        a, b, f, g = to_dev(f1, f2, flow, go)
+        a.requires_grad_(); b.requires_grad_(); f.requires_grad_()
+        if concat:
+            est = PF.warp_correlation_concat(a, b, f if with_flow else None, None if with_flow else f, *cfg,
+                                             act=act, slope=0.01)
+        else:
+            corr = PF.warp_correlation(a, b, f if with_flow else None, *cfg, act=act, slope=0.01)
+            est = torch.cat([a, corr, f], dim=1)
+        est.backward(g)
+        torch.cuda.synchronize()
+        res.append((est.detach(), a.grad, b.grad, f.grad))
+    for got, want in zip(*res):
+        assert max_rel(got.cpu().numpy(), want.cpu().numpy()) < 2e-6
+    # and against the oracle
+    ref = co.warpcorr_forward(f1, f2, flow if with_flow else None, *cfg, act=act, slope=0.01) if with_flow else \
+        co.corr_forward(f1, f2, *cfg)
+    if not with_flow and act:
+        ref = np.where(ref < 0, ref * np.float32(0.01), ref)
+    assert max_rel(res[0][0][:, C:C + D2].cpu().numpy(), ref) < TOL
+
+
+def test_training_step_with_direct_concat_equals_cat_path():
+    """Net under autograd: the concat-buffer path (default) against the torch.cat path, loss and gradients."""
+    from pwc_net_pytorch_b200.model import Net, default_args
+    from pwc_net_pytorch_b200.workloads import multiscale_l1
+    from oracle.model_ops import deterministic_init
+    torch.backends.cudnn.allow_tf32 = False
+    for over in ({}, {"corr_activation": True, "residual": True}):
+        net = Net(default_args(device="cuda", **over)).train()
+        deterministic_init(net, seed=4)
+        g = torch.Generator().manual_seed(5)
+        x = (torch.rand(2, 3, 2, 128, 192, generator=g) * 255.0).cuda()
+        gt = (torch.randn(2, 2, 128, 192, generator=g) * 3.0).cuda()
+        out = []
+        for direct in (True, False):
+            net._direct_concat = direct
+            net.zero_grad()
+            flows, _ = net(x)
+            loss = multiscale_l1(flows, gt)
+            loss.backward()
+            out.append((float(loss.detach()), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+        assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[1][0])
+        assert out[0][1].keys() == out[1][1].keys()
+        for k in out[0][1]:
+            a, b = out[0][1][k], out[1][1][k]
+            assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12, k
