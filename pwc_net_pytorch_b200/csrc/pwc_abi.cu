@@ -71,6 +71,22 @@ bool fast_path(const pwc::CorrGeom& g)
            (g.s2 == 1 || g.s2 == 2);
 }
 
+constexpr int B200_SMS = 148;      // only the fallback when the attribute query fails
+
+// SM count of the current device (cached per thread and device): every launch heuristic sizes its grid from it
+int sm_count_of_current_device()
+{
+    static thread_local int dev_cached = -1, count = B200_SMS;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) {
+        if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) count = B200_SMS;
+        (void)cudaGetLastError();
+        dev_cached = dev;
+    }
+    return count;
+}
+
 // Where the forward kernels take the flow from (model.py:74-80):
 //   flow   : [2][H][W] per image, image n at flow + n * fbs floats (fbs == 2*H*W when dense), or NULL (no warp)
 //   coarse : when non-NULL, the previous level's flow [B][2][H/2][W/2] (dense); the kernel evaluates
@@ -104,7 +120,7 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, long l
     // few tiles but many channels (small pyramid levels): split the channels over a thread-block
     // cluster of up to 8 CTAs per tile (deterministic DSMEM reduction inside the kernel)
     int ksplit = 1;
-    while (ksplit < 8 && blocks * ksplit < 148 && g.C / (ksplit * 2) >= 8) ksplit *= 2;
+    while (ksplit < 8 && blocks * ksplit < sm_count_of_current_device() && g.C / (ksplit * 2) >= 8) ksplit *= 2;
     const int cper = pwc::cdiv(g.C, ksplit);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(blocks * ksplit));
@@ -127,19 +143,6 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, long l
 
 // ---- whole-image path for the coarse levels (small_image.cuh) -----------------------------------
 constexpr size_t SMALL_SMEM_LIMIT = 200 * 1024;
-
-int sm_count_of_current_device()
-{
-    static thread_local int dev_cached = -1, count = 148;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != dev_cached) {
-        if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) count = 148;
-        (void)cudaGetLastError();
-        dev_cached = dev;
-    }
-    return count;
-}
 
 pwc::SmallPlan small_plan_for(const pwc::CorrGeom& g, bool has_flow, bool backward)
 {
@@ -290,9 +293,7 @@ int launch_fwd_tma(const float* f1, const float* f2, const FlowSpec& fs, float* 
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long ntiles = (long long)tiles_x * tiles_y * g.B;
     if (ntiles > 0x3fffffffLL) return fail("grid too large");
-    static thread_local int sm_count = 0;
-    if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        sm_count = 148;
+    const int sm_count = sm_count_of_current_device();
     // persistent: one CTA per SM (148 on B200), each walks tiles blockIdx.x, blockIdx.x + grid, ...
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     kern<<<grid, Cfg::NT, smem, st>>>(m1, m2, m3, f2, flow, out, warped, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles,
@@ -415,7 +416,7 @@ int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, f
     if (blocks > 0x7fffffffLL) return fail("grid too large");
     // split the (independent) output channels over blockIdx.y until the grid covers ~2 waves
     int cgroup = g.C;
-    while (cgroup > Cfg::CK && blocks * pwc::cdiv(g.C, cgroup) < 296) cgroup = pwc::round_up(pwc::cdiv(cgroup, 2), Cfg::CK);
+    while (cgroup > Cfg::CK && blocks * pwc::cdiv(g.C, cgroup) < 2 * sm_count_of_current_device()) cgroup = pwc::round_up(pwc::cdiv(cgroup, 2), Cfg::CK);
     const dim3 grid((unsigned)blocks, (unsigned)pwc::cdiv(g.C, cgroup));
     kern<<<grid, Cfg::NT, smem, st>>>(gout, gate, X, res, g.C, g.H, g.W, tiles_x, tiles_y, cgroup, slope, gbs, gate_bs);
     return check_launch("corr_bwd_kernel");
@@ -445,9 +446,7 @@ int launch_bwd_tma(const float* gout, long long gbs, const float* X, float* res,
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long ntiles = (long long)tiles_x * tiles_y * g.B;
     if (ntiles > 0x3fffffffLL) return fail("grid too large");
-    static thread_local int sm_count = 0;
-    if (sm_count == 0 && cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        sm_count = 148;
+    const int sm_count = sm_count_of_current_device();
     const unsigned grid = (unsigned)(ntiles < sm_count ? ntiles : sm_count);
     kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)ntiles, gbs);
     return check_launch("corr_bwd_tma_kernel");
@@ -592,7 +591,7 @@ int scatter_zero(float* scratch, float* grad_flow, int B, int C, int H, int W, c
 {
     const size_t n8 = (size_t)B * pwc::cdiv(C, 8) * H * W * 8, nf = (size_t)B * 2 * H * W;
     if ((nf & 3) == 0 && (((uintptr_t)scratch | (uintptr_t)grad_flow) & 15) == 0) {
-        const unsigned grid = (unsigned)std::min<size_t>((n8 / 4 + nf / 4 + 255) / 256, (size_t)148 * 8);
+        const unsigned grid = (unsigned)std::min<size_t>((n8 / 4 + nf / 4 + 255) / 256, (size_t)sm_count_of_current_device() * 8);
         if (launch_into_tail(pwc::zero2_kernel, dim3(grid), dim3(256), stream, reinterpret_cast<float4*>(scratch), n8 / 4,
                              reinterpret_cast<float4*>(grad_flow), nf / 4) != cudaSuccess)
             return fail("zero2_kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
@@ -711,7 +710,7 @@ int pwc_warp_backward(const float* grad_out, const float* x, const float* flow, 
         return fail("cudaMemsetAsync(grad_x): %s", cudaGetErrorString(cudaGetLastError()));
     // channel groups in parallel; the flow gradient is then a sum over groups (atomicAdd on a zeroed buffer)
     int cpt = C;
-    while (cpt > 8 && (size_t)B * H * W * pwc::cdiv(C, cpt) < (size_t)148 * 2048) cpt = pwc::cdiv(cpt, 2);
+    while (cpt > 8 && (size_t)B * H * W * pwc::cdiv(C, cpt) < (size_t)sm_count_of_current_device() * 2048) cpt = pwc::cdiv(cpt, 2);
     const int cgroups = pwc::cdiv(C, cpt);
     if (grad_flow && cgroups > 1 &&
         cudaMemsetAsync(grad_flow, 0, sizeof(float) * (size_t)B * 2 * H * W, stream) != cudaSuccess)

@@ -184,6 +184,407 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int tiles
     return t;
 }
 
+// Ring-slot counter (slot index + phase parity of the slot's current use), advanced per work item: the roles walk
+// their streams of (tile, chunk) items with increments only.  Measured (ncu source view, level-2 shape): the integer
+// divisions of `g / nchunks`, `g % NS` and of tile_coord(), re-evaluated per chunk, were ~40% of the bilinear
+// role's dependent instruction chain, and that role is the one the correlation warps wait for.
+template <int N>
+struct Ring {
+    int slot = 0, phase = 0;
+    __device__ __forceinline__ void next()
+    {
+        if (++slot == N) { slot = 0; phase ^= 1; }
+    }
+};
+// (local tile, chunk) cursor of a role's item stream; the tile coordinate is recomputed once per tile
+struct ItemCursor {
+    int lt = 0, k = 0;
+    TileCoord tc;
+    __device__ __forceinline__ void start(int tiles_x, int tiles_y, int TH, int TW)
+    {
+        tc = tile_coord(blockIdx.x, tiles_x, tiles_y, TH, TW);
+    }
+    __device__ __forceinline__ void next(int nchunks, int tiles_x, int tiles_y, int TH, int TW)
+    {
+        if (++k == nchunks) {
+            k = 0;
+            ++lt;
+            tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+        }
+    }
+};
+
+// Cold path of the bilinear role: a sample whose 2x2 footprint lies outside the staged window is gathered from
+// global memory (correctness never depends on the flow magnitude).  The flow comes from `flow` (batch stride fbs) or
+// is evaluated from `coarse` (model.py:78 folded in).  vv[c] = warped f2[n, c0 + c] at pixel (x, y), 0 beyond C.
+template <int CK>
+__device__ __noinline__ void global_tap_values(float* vv, const float* __restrict__ f2, const float* __restrict__ flow,
+                                               long long fbs, const float* __restrict__ coarse, int n, int x, int y,
+                                               int c0, int C, int H, int W)
+{
+    const size_t HW = (size_t)H * W;
+    float fu, fv;
+    if (coarse != nullptr) {
+        const int Hc = H >> 1, Wc = W >> 1;
+        const float* cu = coarse + (size_t)n * 2 * Hc * Wc;
+        up2_flow_at(cu, cu + Hc * Wc, Hc, Wc, x, y, fu, fv);
+    } else {
+        const float* un = flow + (size_t)n * (size_t)fbs;
+        fu = __ldg(un + (size_t)y * W + x);
+        fv = __ldg(un + HW + (size_t)y * W + x);
+    }
+    const Tap tp = make_tap(x, y, fu, fv, H, W);
+#pragma unroll
+    for (int c = 0; c < CK; ++c)
+        vv[c] = (c0 + c < C && tp.off >= 0) ? tap_sample(tp, f2 + ((size_t)n * C + c0 + c) * HW) : 0.0f;
+}
+
+#ifndef PWC_ROLE_ATTR
+#define PWC_ROLE_ATTR __forceinline__
+#endif
+
+// Kernel arguments as one record: the producer roles are compiled as separate (non-inlined) functions, so that their
+// register allocation is independent of the correlation role, which fills the 128-register budget of a 512-thread
+// CTA on its own.  (With every role inlined, values of the common prologue were spilled to local memory and reloaded
+// inside the producer loops -- measured: 180-280 bytes of spills once the loops kept their cursors in registers.)
+struct FwdArgs {
+    const CUtensorMap *tmF1, *tmF2, *tmFlow;
+    const float *f2, *flow;
+    float *out, *warped_out;
+    int C, H, W, tiles_x, tiles_y, ntiles, act;
+    float slope;
+    long long obs, fbs;
+    const float* coarse;
+    float* flow_out;
+    long long fobs;
+};
+
+// The context every role derives for itself: compile-time geometry, the shared-memory carve-up (declared from the
+// extern array in each function, so the accesses stay LDS/STS), and this CTA's share of the work.
+#define PWC_FWD_CTX(A)                                                                                             \
+    const CUtensorMap& tmF1 = *(A).tmF1; const CUtensorMap& tmF2 = *(A).tmF2; const CUtensorMap& tmFlow = *(A).tmFlow;  \
+    const float* __restrict__ f2 = (A).f2; const float* __restrict__ flow = (A).flow; float* __restrict__ out = (A).out;\
+    float* __restrict__ warped_out = (A).warped_out; const int C = (A).C, H = (A).H, W = (A).W;                         \
+    const int tiles_x = (A).tiles_x, tiles_y = (A).tiles_y, ntiles = (A).ntiles, act = (A).act; const float slope = (A).slope;\
+    const long long obs = (A).obs, fbs = (A).fbs, fobs = (A).fobs; const float* __restrict__ coarse = (A).coarse;       \
+    float* __restrict__ flow_out = (A).flow_out;                                                                        \
+    constexpr int D = Cfg::D, S2 = Cfg::S2, CK = Cfg::CK, PX = Cfg::PX, R = Cfg::R;                                     \
+    constexpr int TW = Cfg::TW, TH = Cfg::TH, HH = Cfg::HH, HWD = Cfg::HWD;                                             \
+    constexpr int WP = Cfg::WP, WW = Cfg::WW, WH = Cfg::WH, F1W = Cfg::F1W, F1H = Cfg::F1H;                             \
+    constexpr int NHALO = Cfg::NHALO, WSPAN = Cfg::WSPAN, NCONS = Cfg::NCONS, NBIL = Cfg::NBIL;                         \
+    constexpr int NS = Cfg::NS, NF1 = Cfg::NF1, NWIN = Cfg::NWIN, PXB = Cfg::PXB, PXP = Cfg::PXP;                       \
+    extern __shared__ __align__(1024) uint8_t base[];                                                                   \
+    uint64_t* barF1 = reinterpret_cast<uint64_t*>(base);                                                                \
+    uint64_t* barF1Free = barF1 + NF1;                                                                                  \
+    uint64_t* barFull = barF1Free + NF1;                                                                                \
+    uint64_t* barEmpty = barFull + NS;                                                                                  \
+    uint64_t* barWin = barEmpty + NS;                                                                                   \
+    uint64_t* barWinFree = barWin + NWIN;                                                                               \
+    uint64_t* barFlow = barWinFree + NWIN;                                                                              \
+    uint64_t* barFlowFree = barFlow + 2;                                                                                \
+    uint64_t* barTaps = barFlowFree + 2;                                                                                \
+    uint64_t* barTapsFree = barTaps + 2;                                                                                \
+    int* worg = reinterpret_cast<int*>(base + Cfg::NBARS * 8);                                                          \
+    float* sF1 = reinterpret_cast<float*>(base + Cfg::CTRL_BYTES);                                                      \
+    float* sW2 = sF1 + NF1 * Cfg::F1_ELEMS;                                                                             \
+    float* sWin = sW2 + NS * Cfg::W2_ELEMS;                                                                             \
+    float* sFlow = sWin + NWIN * Cfg::WIN_ELEMS;                                                                        \
+    float4* sTapW = reinterpret_cast<float4*>(sFlow + 2 * Cfg::FLOW_ELEMS);                                             \
+    int* sTapM = reinterpret_cast<int*>(sTapW + 2 * NHALO);                                                             \
+    const int tid = threadIdx.x;                                                                                        \
+    const size_t HW = (size_t)H * W;                                                                                    \
+    const int nchunks = (C + CK - 1) / CK;                                                                              \
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;          \
+    const int total = my_tiles * nchunks;                                                                               \
+    (void)tmF1; (void)tmF2; (void)tmFlow; (void)f2; (void)flow; (void)out; (void)warped_out; (void)act; (void)slope; (void)obs; (void)fbs; (void)fobs; (void)coarse; (void)flow_out; (void)barF1; (void)barF1Free; (void)barFull; (void)barEmpty; (void)barWin; (void)barWinFree; (void)barFlow; (void)barFlowFree; (void)barTaps; (void)barTapsFree; (void)worg; (void)sF1; (void)sW2; (void)sWin; (void)sFlow; (void)sTapW; (void)sTapM; (void)HW; (void)total; (void)tid; (void)H; (void)W;
+
+// ================================ T: TMA issue warp (one thread) ================================
+template <class Cfg, bool HAS_FLOW>
+__device__ PWC_ROLE_ATTR void fwd_role_tma(const FwdArgs& A)
+{
+    PWC_FWD_CTX(A)
+    // ================================ T: TMA issue warp ================================
+    if (tid != NCONS + NBIL + 32) return;
+    prefetch_tmap(&tmF1);
+    prefetch_tmap(&tmF2);
+    ItemCursor cf;                        // next f1 chunk to request
+    Ring<NF1> rf;
+    cf.start(tiles_x, tiles_y, TH, TW);
+    int nf = 0;                           // f1 chunks requested so far
+    auto request_f1 = [&]() {             // f1 chunk of the next work item -> its ring slot
+        if (nf >= NF1) mbar_wait(&barF1Free[rf.slot], rf.phase ^ 1);      // item nf - NF1 consumed
+        mbar_expect_tx(&barF1[rf.slot], Cfg::F1_BYTES);
+        tma_load_4d(sF1 + rf.slot * Cfg::F1_ELEMS, &tmF1, &barF1[rf.slot], cf.tc.x0, cf.tc.y0, cf.k * CK, cf.tc.n);
+        cf.next(nchunks, tiles_x, tiles_y, TH, TW);
+        rf.next();
+        ++nf;
+    };
+    if (!HAS_FLOW) {
+        // plain correlation: the f2 tile + halo *is* the warped chunk; TMA writes it directly
+        for (int j = 0; j < NS && j < total; ++j) request_f1();
+        ItemCursor cw;
+        Ring<NS> rs;
+        cw.start(tiles_x, tiles_y, TH, TW);
+        for (int g = 0; g < total; ++g) {
+            if (nf < total) request_f1();
+            if (g >= NS) mbar_wait(&barEmpty[rs.slot], rs.phase ^ 1);
+            mbar_expect_tx(&barFull[rs.slot], Cfg::W2_BYTES);
+            tma_load_4d(sW2 + rs.slot * Cfg::W2_ELEMS, &tmF2, &barFull[rs.slot], cw.tc.x0 - R, cw.tc.y0 - R, cw.k * CK,
+                        cw.tc.n);
+            cw.next(nchunks, tiles_x, tiles_y, TH, TW);
+            rs.next();
+        }
+        return;
+    }
+    prefetch_tmap(&tmFlow);
+    auto request_flow = [&](int lt) {    // flow tile + halo of local tile lt -> sFlow[lt & 1]
+        const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+        if (coarse != nullptr) {         // the coarse box that covers the tile + halo
+            mbar_expect_tx(&barFlow[lt & 1], Cfg::CFLOW_BYTES);
+            tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 / 2 - Cfg::CW_OFF,
+                        tj.y0 / 2 - Cfg::CH_OFF, 0, tj.n);
+        } else {
+            mbar_expect_tx(&barFlow[lt & 1], Cfg::FLOW_BYTES);
+            tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 - R, tj.y0 - R, 0, tj.n);
+        }
+    };
+    if (my_tiles > 0) request_flow(0);
+    if (my_tiles > 1) request_flow(1);
+    for (int j = 0; j < NS && j < total; ++j) request_f1();
+    int wx0 = 0, wy0 = 0;
+    int jw = 0;             // next work item whose f2 window has not been requested
+    ItemCursor cw;
+    Ring<NWIN> rw;
+    cw.start(tiles_x, tiles_y, TH, TW);
+    for (int g = 0; g < total; ++g) {
+        if (nf < total) request_f1();
+        for (; jw < total && jw < g + NWIN; ++jw) {
+            if (cw.k == 0) {             // first chunk of a tile: its window origin comes from the taps warp
+                const int lt = cw.lt;
+                if (lt + 1 < my_tiles && lt + 1 >= 2) {
+                    mbar_wait(&barFlowFree[(lt + 1) & 1], ((lt - 1) >> 1) & 1);   // P is done with tile lt - 1's flow
+                    request_flow(lt + 1);
+                }
+                mbar_wait(&barTaps[lt & 1], (lt >> 1) & 1);
+                wx0 = worg[2 * (lt & 1)]; wy0 = worg[2 * (lt & 1) + 1];
+            }
+            if (jw >= NWIN) mbar_wait(&barWinFree[rw.slot], rw.phase ^ 1);   // B is done with item jw - NWIN
+            mbar_expect_tx(&barWin[rw.slot], Cfg::WIN_BYTES);
+            tma_load_4d(sWin + rw.slot * Cfg::WIN_ELEMS, &tmF2, &barWin[rw.slot], wx0, wy0, cw.k * CK, cw.tc.n);
+            cw.next(nchunks, tiles_x, tiles_y, TH, TW);
+            rw.next();
+        }
+    }
+    return;
+}
+
+// ================================ P: taps warp ================================
+template <class Cfg, bool HAS_FLOW>
+__device__ PWC_ROLE_ATTR void fwd_role_taps(const FwdArgs& A)
+{
+    PWC_FWD_CTX(A)
+    // ================================ P: taps warp ================================
+    if (!HAS_FLOW) return;
+    const int lane = tid & 31;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+        const int par = lt & 1;
+        const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+        mbar_wait(&barFlow[par], (lt >> 1) & 1);
+        if (lt >= 2) mbar_wait(&barTapsFree[par], ((lt >> 1) - 1) & 1);   // B finished tile lt - 2
+        const float* sfl = sFlow + par * Cfg::FLOW_ELEMS;
+        float4* tapW = sTapW + par * NHALO;
+        int* tapM = sTapM + par * NHALO;
+        // pass 1: sample positions of tile + halo and their bounding box (pixels outside the image are
+        // skipped by coordinate; the TMA zero fill of the flow tile is never interpreted)
+        int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -0x7fffffff, mxy = -0x7fffffff;
+#pragma unroll 4
+        for (int j = 0; j < PXP; ++j) {
+            const int i = lane + 32 * j;
+            if (i < NHALO) {
+                const int hy = i / HWD, hx = i - hy * HWD;
+                const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                int meta = TAP_EMPTY;
+                if (y >= 0 && y < H && x >= 0 && x < W) {
+                    float u, v;
+                    if (coarse != nullptr) {
+                        constexpr int CWB = Cfg::CWB, CPL = Cfg::CHB * Cfg::CWB;
+                        int xl, xr, yl, yr;
+                        const float lx1 = up2_source(x, W >> 1, xl, xr), ly1 = up2_source(y, H >> 1, yl, yr);
+                        const int cx0 = tc.x0 / 2 - Cfg::CW_OFF, cy0 = tc.y0 / 2 - Cfg::CH_OFF;
+                        const int ia = (yl - cy0) * CWB + (xl - cx0), ib = (yl - cy0) * CWB + (xr - cx0);
+                        const int ic = (yr - cy0) * CWB + (xl - cx0), id = (yr - cy0) * CWB + (xr - cx0);
+                        u = up2_blend(sfl[ia], sfl[ib], sfl[ic], sfl[id], lx1, ly1);
+                        v = up2_blend(sfl[CPL + ia], sfl[CPL + ib], sfl[CPL + ic], sfl[CPL + id], lx1, ly1);
+                        if (flow_out != nullptr && hy >= R && hy < R + TH && hx >= R && hx < R + TW) {
+                            float* fo = flow_out + (size_t)tc.n * (size_t)fobs + (size_t)y * W + x;
+                            fo[0] = u;
+                            fo[HW] = v;
+                        }
+                    } else {
+                        u = sfl[i];
+                        v = sfl[NHALO + i];
+                    }
+                    if (fabsf(u) < 1.0e6f && fabsf(v) < 1.0e6f) {          // rejects NaN / Inf as well
+                        // floor + fraction of the flow first: the fraction is exact in fp32 (pwc_common.cuh)
+                        const float fu = floorf(u), fv = floorf(v);
+                        const float ax = u - fu, ay = v - fv;
+                        const int x0 = x + (int)fu, y0 = y + (int)fv;
+                        if (x0 >= -1 && x0 < W && y0 >= -1 && y0 < H) {
+                            w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
+                            meta = ((y0 + 1) << 16) | (x0 + 1);   // x0, y0 >= -1; H, W < 32760 (host check)
+                            mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
+                            mny = min(mny, y0); mxy = max(mxy, y0 + 1);
+                        }
+                    }
+                }
+                tapW[i] = w;
+                tapM[i] = meta;
+            }
+        }
+        mbar_arrive(&barFlowFree[par]);      // this lane no longer reads sFlow[par]
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        // window origin: the bounding box if it fits, else centred on it (outliers -> global gather)
+        int wx0 = 0, wy0 = 0;
+        if (mnx <= mxx) {
+            wx0 = mnx & ~3;                                   // 16-byte aligned TMA start (also for x < 0)
+            if (mxx - wx0 + 1 > WW) wx0 = ((mnx + mxx + 1 - WW) >> 1) & ~3;
+            wy0 = (mxy - mny + 1 <= WH) ? mny : (mny + mxy + 1 - WH) / 2;
+        }
+        // pass 2: positions -> window-relative offsets (each lane revisits exactly the taps it wrote)
+#pragma unroll 4
+        for (int j = 0; j < PXP; ++j) {
+            const int i = lane + 32 * j;
+            if (i < NHALO) {
+                const int meta = tapM[i];
+                if (meta >= 0) {
+                    const int x0 = (meta & 0xffff) - 1, y0 = (meta >> 16) - 1;
+                    const int rx = x0 - wx0, ry = y0 - wy0;
+                    tapM[i] = (rx >= 0 && rx + 1 < WW && ry >= 0 && ry + 1 < WH) ? ry * WW + rx : TAP_GLOBAL;
+                }
+            }
+        }
+        if (lane == 0) { worg[2 * par] = wx0; worg[2 * par + 1] = wy0; }
+        mbar_arrive(&barTaps[par]);          // release: taps[par] and worg[par] are complete
+    }
+    return;
+}
+
+// ================================ B: bilinear warps ================================
+template <class Cfg, bool HAS_FLOW>
+__device__ PWC_ROLE_ATTR void fwd_role_bilinear(const FwdArgs& A)
+{
+    PWC_FWD_CTX(A)
+    // ================================ B: bilinear warps ================================
+    if (!HAS_FLOW) return;
+    const int btid = tid - NCONS;
+    float4 tw[PXB];          // this thread's taps for the current tile (registers for all its chunks)
+    int toff[PXB];           // window offset (0 for empty taps: weights are 0), or TAP_NONE / TAP_GLOBAL
+    int tdst[PXB];           // destination offset in the warped chunk
+    bool any_global = false;
+    Ring<NS> rs;             // warped-chunk ring
+    Ring<NWIN> rw;           // f2 window ring
+    int g = 0;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+        const int par = lt & 1;
+        mbar_wait(&barTaps[par], (lt >> 1) & 1);
+        any_global = false;
+#pragma unroll
+        for (int j = 0; j < PXB; ++j) {
+            const int i = btid + j * NBIL;
+            const bool valid = i < NHALO;
+            const int ii = valid ? i : 0;
+            int hy, hx;
+            halo_item<HWD>(ii, hy, hx);
+            tw[j] = sTapW[par * NHALO + hy * HWD + hx];
+            const int meta = sTapM[par * NHALO + hy * HWD + hx];
+            tdst[j] = hy * WP + hx;
+            toff[j] = !valid ? TAP_NONE : (meta == TAP_EMPTY ? 0 : meta);
+            any_global |= valid && meta == TAP_GLOBAL;
+        }
+#pragma unroll 1
+        for (int k = 0; k < nchunks; ++k, ++g) {
+        const int c0 = k * CK;
+        if (g >= NS) mbar_wait(&barEmpty[rs.slot], rs.phase ^ 1);    // consumers released warped slot
+        mbar_wait(&barWin[rw.slot], rw.phase);
+        const float* win = sWin + rw.slot * Cfg::WIN_ELEMS;
+        float* w2buf = sW2 + rs.slot * Cfg::W2_ELEMS;
+        float v[PXB][CK];
+        // The corner loads go out in groups of 8 (two channels of one pixel; the empty asm is a compiler-
+        // level fence that keeps the groups apart).  64 loads per thread in one burst kept the LSU queue
+        // full of this role's conflicting scalar loads, and the consumers' LDS.128 waited behind them:
+        // bursts of 64 / 16 / 8 / 4 loads -> 118.5 / 117.3 / 112.8 / 118.2 us at the level-2 shape.  The
+        // stores stay together at the end (storing each pixel at once: 128 us).
+#pragma unroll
+        for (int j = 0; j < PXB; ++j) {
+            const float* p = win + (toff[j] >= 0 ? toff[j] : 0);     // empty / none / global: a safe address
+#pragma unroll
+            for (int c = 0; c < CK; ++c) {
+                const float* q = p + c * (WH * WW);
+                v[j][c] = fmaf(tw[j].w, q[WW + 1], fmaf(tw[j].z, q[WW], fmaf(tw[j].y, q[1], tw[j].x * q[0])));
+#ifndef PWC_BGROUP
+#define PWC_BGROUP 2
+#endif
+                if (PWC_BGROUP > 0 && (c % PWC_BGROUP) == PWC_BGROUP - 1) asm volatile("" ::: "memory");
+            }
+        }
+        if (any_global) {
+            // outliers (cold path, its own function so that it costs the loop no registers): recompute the tap
+            // from the flow and gather from global memory
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                if (toff[j] == TAP_GLOBAL) {
+                    const int i = btid + j * NBIL;
+                    int hy, hx;
+                    halo_item<HWD>(i, hy, hx);
+                    float vv[CK];
+                    const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);   // (cold)
+                    global_tap_values<CK>(vv, f2, flow, fbs, coarse, tc.n, tc.x0 - R + hx, tc.y0 - R + hy, c0, C, H, W);
+#pragma unroll
+                    for (int c = 0; c < CK; ++c) v[j][c] = vv[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PXB; ++j) {
+            if (toff[j] != TAP_NONE) {
+                float* dst = w2buf + tdst[j];
+#pragma unroll
+                for (int c = 0; c < CK; ++c) dst[c * (HH * WP)] = v[j][c];
+            }
+        }
+        if (warped_out != nullptr) {     // x2_warp export (model.py:107,113)
+            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                const int i = btid + j * NBIL;
+                int hy, hx;
+                halo_item<HWD>(i < NHALO ? i : 0, hy, hx);
+                const int gy = tc.y0 - R + hy, gx = tc.x0 - R + hx;
+                if (toff[j] != TAP_NONE && hy >= R && hy < R + TH && hx >= R && hx < R + TW && gy < H && gx < W) {
+                    float* wo = warped_out + ((size_t)tc.n * C + c0) * HW + (size_t)gy * W + gx;
+#pragma unroll
+                    for (int c = 0; c < CK; ++c)
+                        if (c0 + c < C) wo[(size_t)c * HW] = v[j][c];
+                }
+            }
+        }
+        mbar_arrive(&barFull[rs.slot]);           // release: this thread's part of the warped chunk is written
+        mbar_arrive(&barWinFree[rw.slot]);        // and it no longer reads this window
+        rs.next();
+        rw.next();
+        }
+        mbar_arrive(&barTapsFree[par]);
+    }
+    return;
+}
+
 template <class Cfg, bool HAS_FLOW>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2,
@@ -257,274 +658,20 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     }
     __syncthreads();     // the only block-wide barrier; roles split below
 
+    FwdArgs A;
+    A.tmF1 = &tmF1; A.tmF2 = &tmF2; A.tmFlow = &tmFlow; A.f2 = f2; A.flow = flow; A.out = out; A.warped_out = warped_out;
+    A.C = C; A.H = H; A.W = W; A.tiles_x = tiles_x; A.tiles_y = tiles_y; A.ntiles = ntiles; A.act = act; A.slope = slope;
+    A.obs = obs; A.fbs = fbs; A.coarse = coarse; A.flow_out = flow_out; A.fobs = fobs;
     if (tid >= NCONS + NBIL + 32) {
-        // ================================ T: TMA issue warp ================================
-        if (tid != NCONS + NBIL + 32) return;
-        prefetch_tmap(&tmF1);
-        prefetch_tmap(&tmF2);
-        auto request_f1 = [&](int j) {       // f1 chunk of work item j -> ring slot j % NF1
-            const TileCoord tj = tile_coord(blockIdx.x + (j / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
-            mbar_expect_tx(&barF1[j % NF1], Cfg::F1_BYTES);
-            tma_load_4d(sF1 + (j % NF1) * Cfg::F1_ELEMS, &tmF1, &barF1[j % NF1], tj.x0, tj.y0, (j % nchunks) * CK, tj.n);
-        };
-        if (!HAS_FLOW) {
-            // plain correlation: the f2 tile + halo *is* the warped chunk; TMA writes it directly
-            for (int j = 0; j < NS && j < total; ++j) request_f1(j);
-            for (int g = 0; g < total; ++g) {
-                const int s = g % NS, jf = g + NS;
-                if (jf < total) {
-                    if (jf >= NF1) mbar_wait(&barF1Free[jf % NF1], ((jf / NF1) - 1) & 1);
-                    request_f1(jf);
-                }
-                const TileCoord tc = tile_coord(blockIdx.x + (g / nchunks) * gridDim.x, tiles_x, tiles_y, TH, TW);
-                if (g >= NS) mbar_wait(&barEmpty[s], ((g / NS) - 1) & 1);
-                mbar_expect_tx(&barFull[s], Cfg::W2_BYTES);
-                tma_load_4d(sW2 + s * Cfg::W2_ELEMS, &tmF2, &barFull[s], tc.x0 - R, tc.y0 - R, (g % nchunks) * CK, tc.n);
-            }
-            return;
-        }
-        prefetch_tmap(&tmFlow);
-        auto request_flow = [&](int lt) {    // flow tile + halo of local tile lt -> sFlow[lt & 1]
-            const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
-            if (coarse != nullptr) {         // the coarse box that covers the tile + halo
-                mbar_expect_tx(&barFlow[lt & 1], Cfg::CFLOW_BYTES);
-                tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 / 2 - Cfg::CW_OFF,
-                            tj.y0 / 2 - Cfg::CH_OFF, 0, tj.n);
-            } else {
-                mbar_expect_tx(&barFlow[lt & 1], Cfg::FLOW_BYTES);
-                tma_load_4d(sFlow + (lt & 1) * Cfg::FLOW_ELEMS, &tmFlow, &barFlow[lt & 1], tj.x0 - R, tj.y0 - R, 0, tj.n);
-            }
-        };
-        if (my_tiles > 0) request_flow(0);
-        if (my_tiles > 1) request_flow(1);
-        for (int j = 0; j < NS && j < total; ++j) request_f1(j);
-        int win_tile = -1;      // last local tile whose window origin has been read
-        int wx0 = 0, wy0 = 0;
-        int jw = 0;             // next work item whose f2 window has not been requested
-        for (int g = 0; g < total; ++g) {
-            const int jf = g + NS;
-            if (jf < total) {
-                if (jf >= NF1) mbar_wait(&barF1Free[jf % NF1], ((jf / NF1) - 1) & 1);   // item jf - NF1 consumed
-                request_f1(jf);
-            }
-            for (; jw < total && jw < g + NWIN; ++jw) {
-                const int lt = jw / nchunks;
-                if (lt > win_tile) {
-                    if (lt + 1 < my_tiles && lt + 1 >= 2) {
-                        mbar_wait(&barFlowFree[(lt + 1) & 1], ((lt - 1) >> 1) & 1);   // P is done with tile lt - 1's flow
-                        request_flow(lt + 1);
-                    }
-                    mbar_wait(&barTaps[lt & 1], (lt >> 1) & 1);
-                    wx0 = worg[2 * (lt & 1)]; wy0 = worg[2 * (lt & 1) + 1];
-                    win_tile = lt;
-                }
-                if (jw >= NWIN) mbar_wait(&barWinFree[jw % NWIN], ((jw / NWIN) - 1) & 1);   // B is done with item jw - NWIN
-                const TileCoord tj = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
-                mbar_expect_tx(&barWin[jw % NWIN], Cfg::WIN_BYTES);
-                tma_load_4d(sWin + (jw % NWIN) * Cfg::WIN_ELEMS, &tmF2, &barWin[jw % NWIN], wx0, wy0,
-                            (jw % nchunks) * CK, tj.n);
-            }
-        }
+        if (tid == NCONS + NBIL + 32) fwd_role_tma<Cfg, HAS_FLOW>(A);
         return;
     }
-
     if (tid >= NCONS + NBIL) {
-        // ================================ P: taps warp ================================
-        if (!HAS_FLOW) return;
-        const int lane = tid & 31;
-        for (int lt = 0; lt < my_tiles; ++lt) {
-            const int par = lt & 1;
-            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
-            mbar_wait(&barFlow[par], (lt >> 1) & 1);
-            if (lt >= 2) mbar_wait(&barTapsFree[par], ((lt >> 1) - 1) & 1);   // B finished tile lt - 2
-            const float* sfl = sFlow + par * Cfg::FLOW_ELEMS;
-            float4* tapW = sTapW + par * NHALO;
-            int* tapM = sTapM + par * NHALO;
-            // pass 1: sample positions of tile + halo and their bounding box (pixels outside the image are
-            // skipped by coordinate; the TMA zero fill of the flow tile is never interpreted)
-            int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -0x7fffffff, mxy = -0x7fffffff;
-#pragma unroll 4
-            for (int j = 0; j < PXP; ++j) {
-                const int i = lane + 32 * j;
-                if (i < NHALO) {
-                    const int hy = i / HWD, hx = i - hy * HWD;
-                    const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
-                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int meta = TAP_EMPTY;
-                    if (y >= 0 && y < H && x >= 0 && x < W) {
-                        float u, v;
-                        if (coarse != nullptr) {
-                            constexpr int CWB = Cfg::CWB, CPL = Cfg::CHB * Cfg::CWB;
-                            int xl, xr, yl, yr;
-                            const float lx1 = up2_source(x, W >> 1, xl, xr), ly1 = up2_source(y, H >> 1, yl, yr);
-                            const int cx0 = tc.x0 / 2 - Cfg::CW_OFF, cy0 = tc.y0 / 2 - Cfg::CH_OFF;
-                            const int ia = (yl - cy0) * CWB + (xl - cx0), ib = (yl - cy0) * CWB + (xr - cx0);
-                            const int ic = (yr - cy0) * CWB + (xl - cx0), id = (yr - cy0) * CWB + (xr - cx0);
-                            u = up2_blend(sfl[ia], sfl[ib], sfl[ic], sfl[id], lx1, ly1);
-                            v = up2_blend(sfl[CPL + ia], sfl[CPL + ib], sfl[CPL + ic], sfl[CPL + id], lx1, ly1);
-                            if (flow_out != nullptr && hy >= R && hy < R + TH && hx >= R && hx < R + TW) {
-                                float* fo = flow_out + (size_t)tc.n * (size_t)fobs + (size_t)y * W + x;
-                                fo[0] = u;
-                                fo[HW] = v;
-                            }
-                        } else {
-                            u = sfl[i];
-                            v = sfl[NHALO + i];
-                        }
-                        if (fabsf(u) < 1.0e6f && fabsf(v) < 1.0e6f) {          // rejects NaN / Inf as well
-                            // floor + fraction of the flow first: the fraction is exact in fp32 (pwc_common.cuh)
-                            const float fu = floorf(u), fv = floorf(v);
-                            const float ax = u - fu, ay = v - fv;
-                            const int x0 = x + (int)fu, y0 = y + (int)fv;
-                            if (x0 >= -1 && x0 < W && y0 >= -1 && y0 < H) {
-                                w = make_float4((1.0f - ax) * (1.0f - ay), ax * (1.0f - ay), (1.0f - ax) * ay, ax * ay);
-                                meta = ((y0 + 1) << 16) | (x0 + 1);   // x0, y0 >= -1; H, W < 32760 (host check)
-                                mnx = min(mnx, x0); mxx = max(mxx, x0 + 1);
-                                mny = min(mny, y0); mxy = max(mxy, y0 + 1);
-                            }
-                        }
-                    }
-                    tapW[i] = w;
-                    tapM[i] = meta;
-                }
-            }
-            mbar_arrive(&barFlowFree[par]);      // this lane no longer reads sFlow[par]
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-                mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-                mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-                mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-            }
-            // window origin: the bounding box if it fits, else centred on it (outliers -> global gather)
-            int wx0 = 0, wy0 = 0;
-            if (mnx <= mxx) {
-                wx0 = mnx & ~3;                                   // 16-byte aligned TMA start (also for x < 0)
-                if (mxx - wx0 + 1 > WW) wx0 = ((mnx + mxx + 1 - WW) >> 1) & ~3;
-                wy0 = (mxy - mny + 1 <= WH) ? mny : (mny + mxy + 1 - WH) / 2;
-            }
-            // pass 2: positions -> window-relative offsets (each lane revisits exactly the taps it wrote)
-#pragma unroll 4
-            for (int j = 0; j < PXP; ++j) {
-                const int i = lane + 32 * j;
-                if (i < NHALO) {
-                    const int meta = tapM[i];
-                    if (meta >= 0) {
-                        const int x0 = (meta & 0xffff) - 1, y0 = (meta >> 16) - 1;
-                        const int rx = x0 - wx0, ry = y0 - wy0;
-                        tapM[i] = (rx >= 0 && rx + 1 < WW && ry >= 0 && ry + 1 < WH) ? ry * WW + rx : TAP_GLOBAL;
-                    }
-                }
-            }
-            if (lane == 0) { worg[2 * par] = wx0; worg[2 * par + 1] = wy0; }
-            mbar_arrive(&barTaps[par]);          // release: taps[par] and worg[par] are complete
-        }
+        if (HAS_FLOW) fwd_role_taps<Cfg, HAS_FLOW>(A);
         return;
     }
-
     if (tid >= NCONS) {
-        // ================================ B: bilinear warps ================================
-        if (!HAS_FLOW) return;
-        const int btid = tid - NCONS;
-        float4 tw[PXB];          // this thread's taps for the current tile (registers for all its chunks)
-        int toff[PXB];           // window offset (0 for empty taps: weights are 0), or TAP_NONE / TAP_GLOBAL
-        int tdst[PXB];           // destination offset in the warped chunk
-        bool any_global = false;
-        for (int g = 0; g < total; ++g) {
-            const int lt = g / nchunks, k = g - lt * nchunks, par = lt & 1, s = g % NS;
-            const int c0 = k * CK;
-            const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
-            if (k == 0) {
-                mbar_wait(&barTaps[par], (lt >> 1) & 1);
-                any_global = false;
-#pragma unroll
-                for (int j = 0; j < PXB; ++j) {
-                    const int i = btid + j * NBIL;
-                    const bool valid = i < NHALO;
-                    const int ii = valid ? i : 0;
-                    int hy, hx;
-                    halo_item<HWD>(ii, hy, hx);
-                    tw[j] = sTapW[par * NHALO + hy * HWD + hx];
-                    const int meta = sTapM[par * NHALO + hy * HWD + hx];
-                    tdst[j] = hy * WP + hx;
-                    toff[j] = !valid ? TAP_NONE : (meta == TAP_EMPTY ? 0 : meta);
-                    any_global |= valid && meta == TAP_GLOBAL;
-                }
-            }
-            if (g >= NS) mbar_wait(&barEmpty[s], ((g / NS) - 1) & 1);    // consumers released warped slot s
-            mbar_wait(&barWin[g % NWIN], (g / NWIN) & 1);
-            const float* win = sWin + (g % NWIN) * Cfg::WIN_ELEMS;
-            float* w2buf = sW2 + s * Cfg::W2_ELEMS;
-            float v[PXB][CK];
-            // The corner loads go out in groups of 8 (two channels of one pixel; the empty asm is a compiler-
-            // level fence that keeps the groups apart).  64 loads per thread in one burst kept the LSU queue
-            // full of this role's conflicting scalar loads, and the consumers' LDS.128 waited behind them:
-            // bursts of 64 / 16 / 8 / 4 loads -> 118.5 / 117.3 / 112.8 / 118.2 us at the level-2 shape.  The
-            // stores stay together at the end (storing each pixel at once: 128 us).
-#pragma unroll
-            for (int j = 0; j < PXB; ++j) {
-                const float* p = win + (toff[j] >= 0 ? toff[j] : 0);     // empty / none / global: a safe address
-#pragma unroll
-                for (int c = 0; c < CK; ++c) {
-                    const float* q = p + c * (WH * WW);
-                    v[j][c] = fmaf(tw[j].w, q[WW + 1], fmaf(tw[j].z, q[WW], fmaf(tw[j].y, q[1], tw[j].x * q[0])));
-                    if (c & 1) asm volatile("" ::: "memory");
-                }
-            }
-            if (any_global) {
-                // outliers: recompute the tap from the flow and gather from global memory
-                const float* un = coarse ? nullptr : flow + (size_t)tc.n * (size_t)fbs;
-                const int Hc = H >> 1, Wc = W >> 1;
-                const float* cu = coarse ? coarse + (size_t)tc.n * 2 * Hc * Wc : nullptr;
-#pragma unroll
-                for (int j = 0; j < PXB; ++j) {
-                    if (toff[j] == TAP_GLOBAL) {
-                        const int i = btid + j * NBIL;
-                        int hy, hx;
-                        halo_item<HWD>(i, hy, hx);
-                        const int y = tc.y0 - R + hy, x = tc.x0 - R + hx;
-                        float fu, fv;
-                        if (coarse != nullptr) {
-                            up2_flow_at(cu, cu + Hc * Wc, Hc, Wc, x, y, fu, fv);
-                        } else {
-                            fu = __ldg(un + (size_t)y * W + x);
-                            fv = __ldg(un + HW + (size_t)y * W + x);
-                        }
-                        const Tap tp = make_tap(x, y, fu, fv, H, W);
-#pragma unroll
-                        for (int c = 0; c < CK; ++c)
-                            v[j][c] = (c0 + c < C && tp.off >= 0)
-                                          ? tap_sample(tp, f2 + ((size_t)tc.n * C + c0 + c) * HW) : 0.0f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < PXB; ++j) {
-                if (toff[j] != TAP_NONE) {
-                    float* dst = w2buf + tdst[j];
-#pragma unroll
-                    for (int c = 0; c < CK; ++c) dst[c * (HH * WP)] = v[j][c];
-                }
-            }
-            if (warped_out != nullptr) {     // x2_warp export (model.py:107,113)
-#pragma unroll
-                for (int j = 0; j < PXB; ++j) {
-                    const int i = btid + j * NBIL;
-                    int hy, hx;
-                    halo_item<HWD>(i < NHALO ? i : 0, hy, hx);
-                    const int gy = tc.y0 - R + hy, gx = tc.x0 - R + hx;
-                    if (toff[j] != TAP_NONE && hy >= R && hy < R + TH && hx >= R && hx < R + TW && gy < H && gx < W) {
-                        float* wo = warped_out + ((size_t)tc.n * C + c0) * HW + (size_t)gy * W + gx;
-#pragma unroll
-                        for (int c = 0; c < CK; ++c)
-                            if (c0 + c < C) wo[(size_t)c * HW] = v[j][c];
-                    }
-                }
-            }
-            mbar_arrive(&barFull[s]);                 // release: this thread's part of warped chunk g is written
-            mbar_arrive(&barWinFree[g % NWIN]);       // and it no longer reads window g % NWIN
-            if (k == nchunks - 1) mbar_arrive(&barTapsFree[par]);
-        }
+        if (HAS_FLOW) fwd_role_bilinear<Cfg, HAS_FLOW>(A);
         return;
     }
 
@@ -535,7 +682,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     // multiply differ from the division by at most 1 ulp, far inside the 1e-5 tolerance)
     const float inv_nelems = __frcp_rn((float)C);
     const bool out_32B_aligned = ((W & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0) && ((obs & 7) == 0);
-    int g = 0;
+    int g = 0;      // (one register: this role sits at the 128-register cap, ring structs here spilled into the FFMA loop)
     for (int lt = 0; lt < my_tiles; ++lt) {
         const TileCoord tc = tile_coord(blockIdx.x + lt * gridDim.x, tiles_x, tiles_y, TH, TW);
         float acc[PX][D];

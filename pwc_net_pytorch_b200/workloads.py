@@ -52,10 +52,13 @@ class TrainStep:
     """
 
     def __init__(self, device, batch=8, height=384, width=448, unused="find", seed=0, args_over=None,
-                 bucket_cap_mb=25):
+                 bucket_cap_mb=25, channels_last=False):
         self.device = torch.device(device)
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.net = Net(default_args(device=self.device, **(args_over or {}))).train()
+        if channels_last:     # conv-stack policy: cuDNN's NHWC kernels, no per-conv layout conversions
+            self.net.to(memory_format=torch.channels_last)
+        self.channels_last = channels_last
         if unused == "freeze":
             for m in unused_estimators(self.net):
                 m.requires_grad_(False)
