@@ -111,7 +111,7 @@ struct TmaCfg {
     static constexpr int PXB = (NHALO + NBIL - 1) / NBIL;  // halo pixels per bilinear thread
     static constexpr int PXP = (NHALO + 31) / 32;          // halo pixels per lane of the taps warp
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 5;                           // warped-chunk ring (B -> C); a slot is released one chunk late (see C)
+    static constexpr int NS = 5;   // warped-chunk ring (B -> C); a slot is released one chunk late (see C)
     static constexpr int NF1 = 8;                          // f1 ring
     static constexpr int NWIN = 3;                         // f2 window ring (T -> B)
     static constexpr int WIN_ELEMS = CK * WH * WW;
