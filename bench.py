@@ -564,12 +564,25 @@ def run_native(args):
         B, C, H, W = SHAPES["level2"]
         ach = fwd_bytes(B, C, H, W) / (fwd_l2_ms * 1e-3) / 1e9
         traffic = None
+        tinfo = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("warpcorr_fwd_level2_dram_bytes")
+                tinfo = json.load(open(tpath))
+                traffic = tinfo.get("warpcorr_fwd_level2_dram_bytes")
             except Exception:
-                traffic = None
+                traffic, tinfo = None, {}
+        # what actually binds the kernel: the shared-memory data pipe, one 128-byte
+        # wavefront per SM and clock; wavefront count from the same ncu capture as `traffic`
+        lsu = None
+        if tinfo.get("warpcorr_fwd_level2_lsu_wavefronts") and clocks.get("sm_max_mhz"):
+            wf = float(tinfo["warpcorr_fwd_level2_lsu_wavefronts"])
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_wf = sms * float(clocks["sm_max_mhz"]) * 1e6
+            lsu = {"resource": "shared-memory data pipe (l1tex__data_pipe_lsu_wavefronts, 1 wavefront = 128 B per SM and clock)",
+                   "wavefronts_per_launch": wf, "peak_wavefronts_per_s": peak_wf,
+                   "min_ms_at_peak": wf / peak_wf * 1e3, "frac": (wf / peak_wf * 1e3) / fwd_l2_ms,
+                   "source": tinfo.get("source")}
         cpu = None
         if not args.no_cpu_baseline:
             cpu = time_cpu_path(5, 1, CPU_SAMPLE_PAIRS)
@@ -589,7 +602,10 @@ def run_native(args):
             "roofline": {
                 "kernel": "warpcorr_fwd_tma_kernel (fused warp+corr forward, level-2 shape B=32 C=32 96x112)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": tinfo.get("source"),
+                "traffic_read_write": [tinfo.get("warpcorr_fwd_level2_dram_read_bytes"),
+                                       tinfo.get("warpcorr_fwd_level2_dram_write_bytes")],
+                "binding_resource": lsu, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fwd_bytes(B, C, H, W), "avg_launch_ms": fwd_l2_ms,
                 "timing": roofline_timing, "avg_launch_ms_alone": fwd_alone_ms,
                 "frac_of_nominal_8000": ach / 8000.0,
@@ -690,12 +706,16 @@ def measure_network_legs(torch, dist, dev, rank, world, dump_kernels=None):
                    "allreduce_bytes": ts.grad_bytes(), "bucket_cap_mb": ts.bucket_cap_mb,
                    "loss_first": first, "loss_last": float(ts.step())}
             if world > 1:
-                ms_local = timed(lambda: ts.step(sync=False), iters=6, warm=1)
                 flat = torch.empty(ts.grad_bytes() // 4, device=dev)
                 ms_ar = timed(lambda: dist.all_reduce(flat), iters=10, warm=3)
-                row.update({"ms_per_step_without_allreduce": ms_local, "allreduce_exposed_ms": ms - ms_local,
-                            "allreduce_alone_ms": ms_ar,
+                row.update({"allreduce_alone_ms": ms_ar,
                             "allreduce_alone_GBps_busbw": ts.grad_bytes() * 2 * (world - 1) / world / ms_ar / 1e6})
+                if unused == "freeze":
+                    # what the collective costs inside the step: the same step with DDP.no_sync() (no all-reduce).
+                    # Not taken with find_unused_parameters=True: there no_sync changes the reducer's bookkeeping
+                    # as well and the comparison is not like for like (measured: the no_sync step is SLOWER).
+                    ms_local = timed(lambda: ts.step(sync=False), iters=6, warm=1)
+                    row.update({"ms_per_step_without_allreduce": ms_local, "allreduce_exposed_ms": ms - ms_local})
                 if unused == "find":
                     row["nccl_kernels"] = profile_nccl(torch, ts, rank, dump_kernels)
             key = "find_unused_parameters" if unused == "find" else ("lv5_lv6_frozen_channels_last" if cl else "lv5_lv6_frozen")
@@ -783,8 +803,11 @@ def profile_nccl(torch, ts, rank, dump_path=None):
                 f.write("# CUDA kernels of 3 DDP training steps (torch.profiler / CUPTI), rank 0: name, launches, total us\n")
                 for k, v in sorted(rows.items(), key=lambda kv: -kv[1][1]):
                     f.write(f"{v[1]:12.1f} us {v[0]:6d} x  {k[:160]}\n")
-        return {"ms_per_step": nccl / 3e3, "share_of_kernel_time": (nccl / total) if total else None,
-                "kernel_ms_per_step": total / 3e3}
+        return {"ms_per_step_incl_peer_wait": nccl / 3e3, "share_of_kernel_time": (nccl / total) if total else None,
+                "kernel_ms_per_step": total / 3e3,
+                "note": "duration of the NCCL all-reduce kernel from CUPTI: it is launched when this rank's bucket is "
+                        "ready and spins until the peer arrives, so it measures rank skew, not transfer time "
+                        "(transfer alone: allreduce_alone_ms)"}
     except Exception as e:
         return {"error": repr(e)}
 
