@@ -111,7 +111,14 @@ struct TmaCfg {
     static constexpr int PXB = (NHALO + NBIL - 1) / NBIL;  // halo pixels per bilinear thread
     static constexpr int PXP = (NHALO + 31) / 32;          // halo pixels per lane of the taps warp
     static constexpr int WSPAN = PX + 2 * R;
-    static constexpr int NS = 5;   // warped-chunk ring (B -> C); a slot is released one chunk late (see C)
+    // Ring depths.  The T warp walks ONE in-order loop over both rings: in iteration g it first waits for the f1 slot
+    // of item g + NS (free once the consumers are past chunk g + NS - NF1 + 1) and only then requests the warped / window
+    // slot of item g, so the operands of item g are requested NF1 - NS - 1 chunks ahead of their use at most.  Measured
+    // at the level-2 shape without a flow (TMA fills the warped ring itself, scripts/dev_fwd.cu): (NS, NF1) = (3,6) 95 us,
+    // (5,8) 95 us, (4,8) 83 us, (4,12) 82 us, (6,8) / (8,10) / (12,14) 137 us -- a lead of 3 chunks hides the TMA latency,
+    // a lead of 1 exposes it in every chunk.  With a flow the bilinear stage sits in between and the depths do not matter
+    // (107.5 - 111.6 us for all of the above).
+    static constexpr int NS = 4;   // warped-chunk ring (B -> C); a slot is released one chunk late (see C)
     static constexpr int NF1 = 8;                          // f1 ring
     static constexpr int NWIN = 3;                         // f2 window ring (T -> B)
     static constexpr int WIN_ELEMS = CK * WH * WW;

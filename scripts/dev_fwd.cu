@@ -54,10 +54,11 @@ static float nrand()
 int main(int argc, char** argv)
 {
     int B = 32, C = 32, H = 96, W = 112, iters = 20;
-    bool smooth = false;
+    bool smooth = false, noflow = false;
     int ai = 1;
     if (argc > 4 && atoi(argv[1]) > 0) { B = atoi(argv[1]); C = atoi(argv[2]); H = atoi(argv[3]); W = atoi(argv[4]); ai = 5; }
     if (argc > ai) smooth = strcmp(argv[ai], "smooth") == 0;
+    if (argc > ai) noflow = strcmp(argv[ai], "noflow") == 0;     // plain correlation: zero flow for the check
     if (argc > ai + 1) iters = atoi(argv[ai + 1]);
     cudaFree(0);
     void* p = nullptr; cudaDriverEntryPointQueryResult q;
@@ -67,7 +68,9 @@ int main(int argc, char** argv)
     std::vector<float> h1(N), h2(N), hf(NF);
     for (auto& v : h1) v = nrand();
     for (auto& v : h2) v = nrand();
-    if (!smooth) {
+    if (noflow) {
+        for (auto& v : hf) v = 0.0f;
+    } else if (!smooth) {
         for (auto& v : hf) v = 2.0f * nrand();
     } else {
         const int ch = H / 8 + 2, cw = W / 8 + 2;
@@ -112,8 +115,9 @@ int main(int argc, char** argv)
     CUtensorMap m1, m2, m3;
     if (!make_map(&m1, d1, B, C, H, W, Cfg::F1W, Cfg::F1H, Cfg::CK) || !make_map(&m2, d2, B, C, H, W, Cfg::WW, Cfg::WH, Cfg::CK) ||
         !make_map(&m3, df, B, 2, H, W, Cfg::HWD, Cfg::HH, 2)) { printf("tensor map failed\n"); return 1; }
-    auto kern = pwc::warpcorr_fwd_tma_kernel<Cfg, true>;
-    const size_t smem = Cfg::smem_bytes(true);
+    auto kern = noflow ? pwc::warpcorr_fwd_tma_kernel<Cfg, false> : pwc::warpcorr_fwd_tma_kernel<Cfg, true>;
+    const size_t smem = Cfg::smem_bytes(!noflow);
+    if (noflow && !make_map(&m2, d2, B, C, H, W, Cfg::WP, Cfg::HH, Cfg::CK)) { printf("tensor map failed\n"); return 1; }
     CK_(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_x = pwc::cdiv(W, Cfg::TW), tiles_y = pwc::cdiv(H, Cfg::TH);
     const int ntiles = tiles_x * tiles_y * B;
@@ -124,9 +128,9 @@ int main(int argc, char** argv)
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f, sum = 0.0f;
     for (int it = 0; it < iters + 3; ++it) {
-        CK_(cudaMemsetAsync(dflush, it & 255, FL));     // evict the inputs from L2 between iterations
+        if (!getenv("DEV_NOFLUSH")) CK_(cudaMemsetAsync(dflush, it & 255, FL));     // evict the inputs from L2 between iterations
         cudaEventRecord(e0);
-        kern<<<grid, Cfg::NT, smem>>>(m1, m2, m3, d2, df, dout, nullptr, C, H, W, tiles_x, tiles_y, ntiles, 0, 0.0f,
+        kern<<<grid, Cfg::NT, smem>>>(m1, m2, m3, d2, noflow ? nullptr : df, dout, nullptr, C, H, W, tiles_x, tiles_y, ntiles, 0, 0.0f,
                                       (long long)81 * HW, (long long)2 * HW, nullptr, nullptr, 0);
         cudaEventRecord(e1);
         CK_(cudaGetLastError());
@@ -141,7 +145,7 @@ int main(int argc, char** argv)
     for (size_t i = 0; i < NO; ++i) { maxerr = fmax(maxerr, fabs((double)ho[i] - hr[i])); maxref = fmax(maxref, fabs((double)hr[i])); }
     const double bytes = 4.0 * (2 * C + 2 + 81) * B * HW;
     printf("shape %dx%dx%dx%d %s S2=%d CK=%d smem=%zu: mean %.2f us best %.2f us  %.1f GB/s (mean)  frac(6453)=%.3f  max rel err vs tiled %.2e %s\n",
-           B, C, H, W, smooth ? "smooth" : "iid", DEV_S2, DEV_CK, smem, 1e3 * sum / iters, 1e3 * best, bytes / (sum / iters) / 1e6,
+           B, C, H, W, noflow ? "noflow" : smooth ? "smooth" : "iid", DEV_S2, DEV_CK, smem, 1e3 * sum / iters, 1e3 * best, bytes / (sum / iters) / 1e6,
            bytes / (sum / iters) / 1e6 / 6453.1, maxerr / maxref, maxerr / maxref < 2e-6 ? "OK" : "MISMATCH");
     return maxerr / maxref < 2e-6 ? 0 : 2;
 }
