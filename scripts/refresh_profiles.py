@@ -42,7 +42,7 @@ for rep, head in ((f"{R}_level2_fwdbwd", "python scripts/prof_case.py fwdbwd lev
         f"# ncu --set full --clock-control none, one launch per kernel: {head}\n"
         "# summary printed by scripts/ncu_summary.py (cold caches, serialised: use shares and pipe utilisations, not absolute times)\n" + txt)
     if "level2" in rep:
-        rd = wr = None
+        rd = wr = wf = pct = None
         cur = None
         for line in txt.splitlines():
             if line.startswith("=="):
@@ -52,12 +52,22 @@ for rep, head in ((f"{R}_level2_fwdbwd", "python scripts/prof_case.py fwdbwd lev
                     rd = float(line.split("=")[1])
                 if "dram__bytes_write.sum [Mbyte]" in line:
                     wr = float(line.split("=")[1])
+                if "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum " in line:
+                    wf = float(line.split("=")[1])
+                if "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed" in line:
+                    pct = float(line.split("=")[1])
         if rd and wr:
             json.dump({"warpcorr_fwd_level2_dram_bytes": int(round((rd + wr) * 1e6)),
                        "note": f"dram__bytes_read.sum ({rd:.2f} MB) + dram__bytes_write.sum ({wr:.2f} MB) of "
                                "warpcorr_fwd_tma_kernel<TmaCfg<1,4>,true> at B=32 C=32 96x112, one ncu --set full capture "
                                f"(profiles/{rep}_ncu.txt). Reads equal the algorithmic 91.0 MB (f1, f2, flow read once from HBM: "
                                "the 2.25x halo re-reads are served by L2); the part of the 111.5 MB output not yet written back "
-                               "when the kernel ended was still dirty in the 126 MB L2."},
+                               "when the kernel ended was still dirty in the 126 MB L2.",
+                       "warpcorr_fwd_level2_dram_read_bytes": int(round(rd * 1e6)),
+                       "warpcorr_fwd_level2_dram_write_bytes": int(round(wr * 1e6)),
+                       "warpcorr_fwd_level2_lsu_wavefronts": int(wf) if wf else None,
+                       "warpcorr_fwd_level2_lsu_pipe_pct_under_ncu": pct,
+                       "source": f"profiles/{rep}_ncu.txt (one ncu --set full capture of this round's kernel; a static "
+                                 "figure, not measured in the bench run)"},
                       open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print("\n".join(out[:16]))
