@@ -506,6 +506,44 @@ def run_native(args):
     for e in ev_done:
         e.record(main)
 
+    def e2e_compute(b):
+        results = {}
+        for n in ("level2", "level6"):
+            f1, f2, flow, gout = dev_in[b][n]
+            f1.grad = f2.grad = flow.grad = None
+            out = op(f1, f2, flow)
+            out.backward(gout)
+            results[n] = [out.detach(), f1.grad, f2.grad, flow.grad]
+        return results
+
+    # The compute part of the end-to-end step is replayed from one CUDA graph per buffer set as well (the public API is
+    # capturable), so that eight ranks launching from Python on one host do not compete for its cores inside the timed
+    # region; `--eager` keeps the Python launches.  The copies stay outside the graphs: they are the thing measured.
+    e2e_graphs, e2e_static = None, None
+    ev_d2h = [torch.cuda.Event() for _ in range(NBUF)]
+    for e in ev_d2h:
+        e.record(main)
+    if graphs is not None:
+        try:
+            cap = torch.cuda.Stream()
+            cap.wait_stream(main)
+            with torch.cuda.stream(cap):
+                for b in range(NBUF):
+                    e2e_compute(b)
+            main.wait_stream(cap)
+            torch.cuda.synchronize()
+            e2e_graphs, e2e_static = [], []
+            for b in range(NBUF):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    res = e2e_compute(b)
+                e2e_graphs.append(g)
+                e2e_static.append(res)
+            torch.cuda.synchronize()
+        except Exception:
+            e2e_graphs, e2e_static = None, None
+            torch.cuda.synchronize()
+
     def e2e_step(i):
         b = i % NBUF
         with torch.cuda.stream(h2d_s):
@@ -516,20 +554,21 @@ def run_native(args):
                         dst.copy_(src, non_blocking=True)
             ev_in[b].record(h2d_s)
         main.wait_event(ev_in[b])
-        results = {}
-        for n in ("level2", "level6"):
-            f1, f2, flow, gout = dev_in[b][n]
-            f1.grad = f2.grad = flow.grad = None
-            out = op(f1, f2, flow)
-            out.backward(gout)
-            results[n] = [out.detach(), f1.grad, f2.grad, flow.grad]
+        if e2e_graphs is not None:
+            main.wait_event(ev_d2h[b])            # the graph's static results of step i - NBUF have been copied out
+            e2e_graphs[b].replay()
+            results = e2e_static[b]
+        else:
+            results = e2e_compute(b)
         ev_done[b].record(main)
         with torch.cuda.stream(d2h_s):
             d2h_s.wait_event(ev_done[b])
             for n in SHAPES:
                 for r, hdst in zip(results[n], host[n][1]):
                     hdst.copy_(r, non_blocking=True)
-                    r.record_stream(d2h_s)
+                    if e2e_graphs is None:
+                        r.record_stream(d2h_s)
+            ev_d2h[b].record(d2h_s)
 
     e2e_steps = max(3, min(args.steps, 40))
     for i in range(4):
@@ -545,11 +584,13 @@ def run_native(args):
     e_end.record()
     barrier()
     e2e_value, _ = parallel.job_throughput(PAIRS_PER_GPU * e2e_steps, e_start.elapsed_time(e_end), dev)
+    e2e_mode = "cuda_graph_replay" if e2e_graphs is not None else "eager"
 
     # ---- whole-network legs (all ranks) + per-kernel breakdown (rank 0), outside the timed region ----
     extras = {}
     legs = {}
     if not args.no_extras:
+        e2e_graphs = e2e_static = None
         dev_in.clear()       # release the e2e buffers before the network legs
         host.clear()
         torch.cuda.empty_cache()
@@ -572,6 +613,17 @@ def run_native(args):
                 traffic = tinfo.get("warpcorr_fwd_level2_dram_bytes")
             except Exception:
                 traffic, tinfo = None, {}
+        # the compute floor beside the HBM one: 81 * C FMAs per pixel on the fp32 pipe at its
+        # 128 lane-FMA/clk/SM peak, and at the ~57 % a register-tiled band correlation sustains (measured rates in
+        # profiles/r02_forward_limits.txt); at the level-2 shape the latter is 42 us, i.e. 0.74 of the HBM roofline
+        fma_floor = None
+        if clocks.get("sm_max_mhz"):
+            sms_ = torch.cuda.get_device_properties(dev).multi_processor_count
+            B2, C2, H2, W2 = SHAPES["level2"]
+            t_peak = 81.0 * C2 * B2 * H2 * W2 / (sms_ * 128 * float(clocks["sm_max_mhz"]) * 1e6) * 1e3
+            fma_floor = {"ms_at_fma_peak": t_peak, "ms_at_sustained_simt_rate": t_peak / 0.57,
+                         "frac_of_hbm_roofline_reachable": fwd_bytes(*SHAPES["level2"]) / (t_peak / 0.57) / 1e6 / peak,
+                         "source": "profiles/r02_forward_limits.txt"}
         # what actually binds the kernel: the shared-memory data pipe, one 128-byte
         # wavefront per SM and clock; wavefront count from the same ncu capture as `traffic`
         lsu = None
@@ -596,7 +648,8 @@ def run_native(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "launch_mode": e2e_mode},
             "gpu_launches": launches_per_step * args.steps,
             "launch_mode": "cuda_graph_replay" if graphs is not None else "eager",
             "roofline": {
@@ -605,7 +658,7 @@ def run_native(args):
                 "traffic": traffic, "traffic_source": tinfo.get("source"),
                 "traffic_read_write": [tinfo.get("warpcorr_fwd_level2_dram_read_bytes"),
                                        tinfo.get("warpcorr_fwd_level2_dram_write_bytes")],
-                "binding_resource": lsu, "peak_source": peak_src,
+                "binding_resource": lsu, "compute_floor": fma_floor, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fwd_bytes(B, C, H, W), "avg_launch_ms": fwd_l2_ms,
                 "timing": roofline_timing, "avg_launch_ms_alone": fwd_alone_ms,
                 "frac_of_nominal_8000": ach / 8000.0,
@@ -829,6 +882,9 @@ def time_cuda(torch, fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+SM_COUNT_B200 = 148
+
+
 def measure_extras(torch, pkg, dev, sets, make_set):
     """Per-kernel timings (CUDA events, rotating inputs) that explain the headline."""
     from pwc_net_pytorch_b200 import functional as PF
@@ -919,6 +975,14 @@ def measure_extras(torch, pkg, dev, sets, make_set):
             fbytes, bbytes = fwd_bytes(Bl, C, H, W), bwd_bytes(Bl, C, H, W)
             row[tag] = {"fwd_ms": ms_f, "fwd_frac": fbytes / ms_f / 1e6 / peak,
                         "bwd_ms": max(ms_fb - ms_f, 1e-6), "bwd_frac": bbytes / max(ms_fb - ms_f, 1e-6) / 1e6 / peak}
+        # the two floors of the forward: HBM at the measured copy bandwidth, and the fp32 FMA pipe -- at
+        # its 128 lane-FMA/clk/SM peak and at the ~57 % an 81-displacement band correlation sustains in a SIMT register
+        # tiling (profiles/r02_forward_limits.txt: FFMA 1.48 clk in an outer-product pattern, LDS.128 4 clk)
+        fma = 81.0 * C * Bl * H * W
+        hbm_ms = fwd_bytes(Bl, C, H, W) / (peak * 1e6)
+        fma_ms_peak = fma / (SM_COUNT_B200 * 128 * 1.965e9) * 1e3
+        row["fwd_floors_ms"] = {"hbm": hbm_ms, "fma_peak": fma_ms_peak, "fma_sustained_simt": fma_ms_peak / 0.57,
+                                "bound": "fma" if fma_ms_peak / 0.57 > hbm_ms else "hbm"}
         levels[name] = row
     out["levels"] = levels
 

@@ -87,6 +87,19 @@ int sm_count_of_current_device()
     return count;
 }
 
+// The shared-memory opt-in of a kernel (cudaFuncSetAttribute) is per (function, device).  Every launcher keeps one bit per
+// device in a static of its own template instantiation: set once per device, for all host threads, without re-setting
+// the attribute when a thread alternates between devices.  (cudaFuncSetAttribute is idempotent, so a race between two
+// first callers is harmless.)
+inline bool device_configured(const std::atomic<unsigned long long>& mask, int dev)
+{
+    return (mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull;
+}
+inline void mark_device_configured(std::atomic<unsigned long long>& mask, int dev)
+{
+    mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+}
+
 // Where the forward kernels take the flow from (model.py:74-80):
 //   flow   : [2][H][W] per image, image n at flow + n * fbs floats (fbs == 2*H*W when dense), or NULL (no warp)
 //   coarse : when non-NULL, the previous level's flow [B][2][H/2][W/2] (dense); the kernel evaluates
@@ -106,13 +119,13 @@ int launch_fwd_tiled(const float* f1, const float* f2, const float* flow, long l
 {
     auto kern = pwc::warpcorr_fwd_kernel<Cfg, HAS_FLOW>;
     const size_t smem = Cfg::smem_bytes(HAS_FLOW);
-    static thread_local int configured_dev = -1;
+    static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) {
+    if (!device_configured(configured_devs, dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
-        configured_dev = dev;
+        mark_device_configured(configured_devs, dev);
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long blocks = (long long)tiles_x * tiles_y * g.B;
@@ -157,18 +170,26 @@ pwc::SmallPlan small_plan_for(const pwc::CorrGeom& g, bool has_flow, bool backwa
 template <class Kern, class... Args>
 int launch_small(Kern kern, const char* what, size_t smem, int B, int ks, cudaStream_t st, Args... args)
 {
-    // the shared-memory opt-in is per (function, device): remember which instantiations have it
-    static thread_local const void* configured[16];
-    static thread_local int configured_dev = -1, nconfigured = 0;
+    // the shared-memory opt-in is per (function, device); this launcher is shared by several kernels of one
+    // signature, so it keeps a small per-thread table of (kernel, devices already configured)
+    struct Entry { const void* fn; unsigned long long devs; };
+    static thread_local Entry configured[16];
+    static thread_local int nconfigured = 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) { nconfigured = 0; configured_dev = dev; }
-    bool seen = false;
-    for (int i = 0; i < nconfigured; ++i) seen |= configured[i] == reinterpret_cast<const void*>(kern);
-    if (!seen) {
+    const void* fn = reinterpret_cast<const void*>(kern);
+    Entry* e = nullptr;
+    for (int i = 0; i < nconfigured; ++i)
+        if (configured[i].fn == fn) e = &configured[i];
+    if (e == nullptr && nconfigured < 16) {
+        e = &configured[nconfigured++];
+        e->fn = fn;
+        e->devs = 0;
+    }
+    if (e == nullptr || !((e->devs >> (dev & 63)) & 1ull)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_LIMIT) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", SMALL_SMEM_LIMIT, cudaGetErrorString(cudaGetLastError()));
-        if (nconfigured < 16) configured[nconfigured++] = reinterpret_cast<const void*>(kern);
+        if (e != nullptr) e->devs |= 1ull << (dev & 63);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * ks));
@@ -281,14 +302,14 @@ int launch_fwd_tma(const float* f1, const float* f2, const FlowSpec& fs, float* 
     }
     auto kern = pwc::warpcorr_fwd_tma_kernel<Cfg, HAS_FLOW>;
     const size_t smem = Cfg::smem_bytes(HAS_FLOW);
-    static thread_local int configured_dev = -1;
+    static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) {
+    if (!device_configured(configured_devs, dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured_dev = dev;
+        mark_device_configured(configured_devs, dev);
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long ntiles = (long long)tiles_x * tiles_y * g.B;
@@ -403,13 +424,13 @@ int launch_bwd_tiled_cfg(const float* gout, const float* gate, const float* X, f
     using Cfg = pwc::BwdCfg<9, S2, 16, TW, TH>;
     auto kern = pwc::corr_bwd_kernel<Cfg, SIGN>;
     const size_t smem = Cfg::smem_bytes();
-    static thread_local int configured_dev = -1;
+    static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) {
+    if (!device_configured(configured_devs, dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
-        configured_dev = dev;
+        mark_device_configured(configured_devs, dev);
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long blocks = (long long)tiles_x * tiles_y * g.B;
@@ -435,13 +456,13 @@ int launch_bwd_tma(const float* gout, long long gbs, const float* X, float* res,
         return -1;
     auto kern = pwc::corr_bwd_tma_kernel<Cfg, SIGN>;
     const size_t smem = Cfg::smem_bytes();
-    static thread_local int configured_dev = -1;
+    static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) {
+    if (!device_configured(configured_devs, dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
-        configured_dev = dev;
+        mark_device_configured(configured_devs, dev);
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const long long ntiles = (long long)tiles_x * tiles_y * g.B;
@@ -464,13 +485,13 @@ int launch_bwd_seq(const float* gout, long long gbs, const float* X, float* res,
         return -1;
     auto kern = pwc::corr_bwd_seq_kernel<SIGN>;
     const size_t smem = Cfg::smem_bytes();
-    static thread_local int configured_dev = -1;
+    static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev) {
+    if (!device_configured(configured_devs, dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
-        configured_dev = dev;
+        mark_device_configured(configured_devs, dev);
     }
     const int tiles_x = pwc::cdiv(g.W, Cfg::TW), tiles_y = pwc::cdiv(g.H, Cfg::TH);
     const int nsc = pwc::cdiv(g.C, Cfg::CPI);
@@ -618,13 +639,13 @@ int scatter_accumulate(const float* grad_out, const float* x, const float* flow,
         if (make_nchw_map(&mX, x, B, C, H, W, Cfg::WW, Cfg::WH, Cfg::CK)) {
             auto kern = pwc::warp_bwd_tile_kernel;
             const size_t smem = Cfg::smem_bytes();
-            static thread_local int configured_dev = -1;
+            static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
             int dev = 0;
             cudaGetDevice(&dev);
-            if (configured_dev != dev) {
+            if (!device_configured(configured_devs, dev)) {
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                     return fail("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(cudaGetLastError()));
-                configured_dev = dev;
+                mark_device_configured(configured_devs, dev);
             }
             const int tiles_x = pwc::cdiv(W, Cfg::TW), tiles_y = pwc::cdiv(H, Cfg::TH);
             const long long ntiles = (long long)tiles_x * tiles_y * B;
