@@ -27,6 +27,8 @@ EXPORTS = (
     "pwc_warp_forward",
     "pwc_warp_backward",
     "pwc_warpcorr_forward",
+    "pwc_warp_backward_workspace",
+    "pwc_warp_backward_ws",
     "pwc_warpcorr_forward_strided",
     "pwc_warpcorr_forward_coarse",
     "pwc_warpcorr_backward_workspace",
@@ -58,6 +60,10 @@ def _declare(L):
     L.pwc_warp_forward.restype = _int
     L.pwc_warp_backward.argtypes = [_c_float_p] * 5 + [_int] * 4 + [_stream]
     L.pwc_warp_backward.restype = _int
+    L.pwc_warp_backward_workspace.argtypes = [_int] * 4
+    L.pwc_warp_backward_workspace.restype = ctypes.c_longlong
+    L.pwc_warp_backward_ws.argtypes = [_c_float_p] * 5 + [_int] * 4 + [ctypes.c_void_p, ctypes.c_longlong, _stream]
+    L.pwc_warp_backward_ws.restype = _int
     L.pwc_warpcorr_forward.argtypes = ([_c_float_p] * 5 + [_int] * 9 + [_int, ctypes.c_float] +
                                        [_stream])
     L.pwc_warpcorr_forward.restype = _int
@@ -105,7 +111,7 @@ def load():
                     "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
             L = ctypes.CDLL(LIB_PATH)
             _declare(L)
-            if L.pwc_abi_version() != 4:
+            if L.pwc_abi_version() != 5:
                 raise RuntimeError("libpwc_b200.so ABI version mismatch; rebuild it")
             _lib = L
     return _lib

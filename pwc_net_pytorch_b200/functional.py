@@ -157,10 +157,20 @@ class WarpFunction(Function):
         B, C, H, W = x.shape
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        L = _lib.load()
         with _on_device(x.device):
-            ok = _lib.load().pwc_warp_backward(_ptr(grad_out), _ptr(x), _ptr(flow), _ptr(gx),
-                                               _ptr(gflow), B, C, H, W, _stream())
-        _lib.check(ok, "pwc_warp_backward")
+            if gx is not None and gflow is not None:
+                # both gradients: the tiled kernel with its 8-channel-interleaved scratch (pwc_b200.h, ABI v5)
+                nbytes = L.pwc_warp_backward_workspace(B, C, H, W)
+                ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=x.device)
+                ok = L.pwc_warp_backward_ws(_ptr(grad_out), _ptr(x), _ptr(flow), _ptr(gx), _ptr(gflow), B, C, H, W,
+                                            ws.data_ptr(), nbytes, _stream())
+                what = "pwc_warp_backward_ws"
+            else:
+                ok = L.pwc_warp_backward(_ptr(grad_out), _ptr(x), _ptr(flow), _ptr(gx), _ptr(gflow), B, C, H, W,
+                                         _stream())
+                what = "pwc_warp_backward"
+        _lib.check(ok, what)
         return gx, gflow
 
 

@@ -41,7 +41,7 @@ def test_library_is_sm100a_only():
 
 def test_abi_version_and_shape_on_cpu():
     L = _lib.load()
-    assert L.pwc_abi_version() == 4
+    assert L.pwc_abi_version() == 5
     assert PF.corr_output_shape(6, 7, 9, 1, 9, 1, 2) == (81, 6, 7)       # README.md:128
     assert PF.corr_output_shape(96, 112, 9, 1, 9, 1, 2) == (81, 96, 112)  # README.md:184
     assert PF.corr_output_shape(96, 112, 4, 1, 4, 1, 1) == (81, 96, 112)

@@ -424,3 +424,71 @@ def test_training_step_with_direct_concat_equals_cat_path():
         for k in out[0][1]:
             a, b = out[0][1][k], out[1][1][k]
             assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12, k
+
+
+# ---- ABI v5: the standalone WarpingLayer on the tiled kernels (forward: warp_bwd_tile_kernel<false>, backward with a
+# ---- caller-owned scratch: pwc_warp_backward_ws) -------------------------------------------------------------------
+WARP_TILE_CASES = [
+    # (shape, flow kind, sigma): tiled path (W % 4 == 0, >= 8 x 16), ragged tiles, outliers beyond the window margin,
+    # coherent large motion, and shapes that must fall back (W % 4 != 0, tiny)
+    ((2, 32, 96, 112), "iid", 2.0), ((1, 13, 40, 52), "iid", 3.0), ((2, 8, 24, 28), "smooth", 6.0),
+    ((1, 5, 33, 36), "iid", 12.0), ((1, 4, 16, 16), "integer", 2.0), ((1, 3, 33, 37), "iid", 3.0),
+    ((2, 192, 6, 7), "iid", 1.0), ((1, 6, 8, 16), "zero", 0.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,kind,sigma", WARP_TILE_CASES)
+def test_standalone_warp_tiled_forward_and_workspace_backward_vs_oracle(shape, kind, sigma):
+    B, C, H, W = shape
+    _, f2, flow, rng = make_inputs(B, C, H, W, seed=77, flow_sigma=sigma, flow_kind=kind)
+    if kind == "smooth":
+        flow = flow + np.float32(9.0)           # large coherent motion on top: the window follows it
+    x, f = to_dev(f2, flow)
+    x.requires_grad_(); f.requires_grad_()
+    y = pkg.WarpingLayer(None)(x, f)
+    assert max_rel(y.detach().cpu().numpy(), co.warp_forward(f2, flow, 0)) < TOL
+    go = rng.standard_normal(f2.shape).astype(np.float32)
+    y.backward(to_dev(go)[0])
+    gx, gf = co.warp_backward(go, f2, flow)
+    assert max_rel(x.grad.cpu().numpy(), gx) < TOL
+    assert max_rel(f.grad.cpu().numpy(), gf) < TOL
+    # the kernels without TMA (plain gathers, scalar reductions) agree with the tiled ones
+    L = _lib.load()
+    L.pwc_set_disable_tma(1)
+    try:
+        x2, f2_ = x.detach().clone().requires_grad_(), f.detach().clone().requires_grad_()
+        y2 = pkg.WarpingLayer(None)(x2, f2_)
+        y2.backward(to_dev(go)[0])
+    finally:
+        L.pwc_set_disable_tma(0)
+    assert max_rel(y2.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-6
+    assert max_rel(x2.grad.cpu().numpy(), x.grad.cpu().numpy()) < TOL
+    assert max_rel(f2_.grad.cpu().numpy(), f.grad.cpu().numpy()) < TOL
+
+
+@pytest.mark.gpu
+def test_warp_backward_ws_argument_handling():
+    """Too small / missing workspace and single-gradient requests take the workspace-free kernel; results agree."""
+    B, C, H, W = 1, 12, 24, 32
+    _, f2, flow, rng = make_inputs(B, C, H, W, seed=78)
+    x, f = to_dev(f2, flow)
+    go = to_dev(rng.standard_normal(f2.shape).astype(np.float32))[0]
+    L = _lib.load()
+    need = L.pwc_warp_backward_workspace(B, C, H, W)
+    assert need == 4 * B * 16 * H * W           # ceil(12 / 8) * 8 channels
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for nbytes in (need, need - 4, 0):
+        ws = torch.empty(max(nbytes, 16) // 4, device=x.device)
+        gx, gf = torch.empty_like(x), torch.empty_like(f)
+        ok = L.pwc_warp_backward_ws(go.data_ptr(), x.data_ptr(), f.data_ptr(), gx.data_ptr(), gf.data_ptr(), B, C, H, W,
+                                    ws.data_ptr() if nbytes else None, nbytes, st)
+        assert ok == 1, _lib.last_error()
+        outs.append((gx, gf))
+    for gx, gf in outs[1:]:
+        assert max_rel(gx.cpu().numpy(), outs[0][0].cpu().numpy()) < TOL
+        assert max_rel(gf.cpu().numpy(), outs[0][1].cpu().numpy()) < TOL
+    gx = torch.empty_like(x)
+    assert L.pwc_warp_backward_ws(go.data_ptr(), x.data_ptr(), f.data_ptr(), gx.data_ptr(), None, B, C, H, W, None, 0, st) == 1
+    assert max_rel(gx.cpu().numpy(), outs[0][0].cpu().numpy()) < TOL
