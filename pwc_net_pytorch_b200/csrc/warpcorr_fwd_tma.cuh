@@ -669,6 +669,34 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     A.tmF1 = &tmF1; A.tmF2 = &tmF2; A.tmFlow = &tmFlow; A.f2 = f2; A.flow = flow; A.out = out; A.warped_out = warped_out;
     A.C = C; A.H = H; A.W = W; A.tiles_x = tiles_x; A.tiles_y = tiles_y; A.ntiles = ntiles; A.act = act; A.slope = slope;
     A.obs = obs; A.fbs = fbs; A.coarse = coarse; A.flow_out = flow_out; A.fobs = fobs;
+#ifndef PWC_REG_SPLIT
+#define PWC_REG_SPLIT 1
+#endif
+    // Register split (setmaxnreg moves registers between groups of 4 warps inside the CTA's launch allocation of
+    // 16 x 32 x 128): warps 12..15 (two bilinear warps, P, T) give up 48 registers each, warps 0..11 (the nine
+    // correlation warps and three bilinear warps) take 16 more -- 12 * 144 + 4 * 80 = 16 * 128.  At 128 registers the
+    // correlation role spilled loop-invariant values and re-read tid (S2R) in every tile's epilogue.  Measured at the
+    // level-2 shape: 111 -> 109 us (i.i.d. flow), 107 -> 105 (smooth), 84 -> 81 (no flow); 152 / 56 makes the bilinear
+    // warps spill (135 us).  stride2 = 2 keeps the plain layout: its bilinear warps hold 7 taps each and spill at 80
+    // registers (162 -> 188 us).
+    if (PWC_REG_SPLIT && Cfg::NT == 512 && Cfg::S2 == 1) {
+        if (tid >= 384) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+            if (tid >= NCONS + NBIL + 32) {
+                if (tid == NCONS + NBIL + 32) fwd_role_tma<Cfg, HAS_FLOW>(A);
+            } else if (tid >= NCONS + NBIL) {
+                if (HAS_FLOW) fwd_role_taps<Cfg, HAS_FLOW>(A);
+            } else {
+                if (HAS_FLOW) fwd_role_bilinear<Cfg, HAS_FLOW>(A);
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+        if (tid >= NCONS) {
+            if (HAS_FLOW) fwd_role_bilinear<Cfg, HAS_FLOW>(A);
+            return;
+        }
+    } else {
     if (tid >= NCONS + NBIL + 32) {
         if (tid == NCONS + NBIL + 32) fwd_role_tma<Cfg, HAS_FLOW>(A);
         return;
@@ -680,6 +708,7 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     if (tid >= NCONS) {
         if (HAS_FLOW) fwd_role_bilinear<Cfg, HAS_FLOW>(A);
         return;
+    }
     }
 
     // ================================ C: correlation warps ================================
