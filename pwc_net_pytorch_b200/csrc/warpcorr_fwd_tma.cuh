@@ -712,8 +712,30 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
     }
 
     // ================================ C: correlation warps ================================
-    const int lane = tid & 31, wd = tid >> 5;     // wd: displacement row, tj = wd - r
-    const int lr = lane & 15, ls = lane >> 4;     // rows fastest: a quarter warp spans 8 rows of one strip
+    // Task of this thread: displacement row wd (tj = wd - r), tile row lr, 8-pixel strip ls.
+    const int lane = tid & 31;
+    int wd, lr, ls;
+#ifndef PWC_QUAD_MAP
+#define PWC_QUAD_MAP 1
+#endif
+    if (PWC_QUAD_MAP && S2 == 1) {
+        // Quad sharing: an LDS.128 costs 4 clocks when all 32 lanes read different words but 2.1 when the lanes of
+        // every aligned group of four read at most two different addresses (equal addresses are merged inside a quad
+        // only, scripts/lds_probe.cu).  A quad = 2 pixel rows x 2 warped rows -- tasks (y, d0), (y, d0+1), (y+1, d0-1),
+        // (y+1, d0) -- reads 2 f1 rows and 2 warped rows; a half warp stacks 4 such row pairs.  d0 = 1, 3, 5, 7 covers
+        // every task except (even row, 0) and (odd row, 8), which the ninth warp takes without sharing.
+        const int w9 = tid >> 5;
+        if (w9 < 8) {
+            const int hw = 2 * w9 + (lane >> 4), qd = (lane >> 2) & 3, e = lane & 3;
+            lr = 8 * (hw >> 3) + 2 * qd + (e >> 1);
+            ls = (hw >> 2) & 1;
+            wd = 1 + 2 * (hw & 3) + (e & 1) - (e >> 1);
+        } else {
+            lr = lane & 15; ls = lane >> 4; wd = (lr & 1) ? D - 1 : 0;
+        }
+    } else {
+        wd = tid >> 5; lr = lane & 15; ls = lane >> 4;     // rows fastest: a quarter warp spans 8 rows of one strip
+    }
     // 1/C (correlation_cuda_kernel.cu:65,100 divide by nelems; a correctly rounded reciprocal and one
     // multiply differ from the division by at most 1 ulp, far inside the 1e-5 tolerance)
     const float inv_nelems = __frcp_rn((float)C);
@@ -726,6 +748,18 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
         for (int p = 0; p < PX; ++p)
 #pragma unroll
             for (int d = 0; d < D; ++d) acc[p][d] = 0.0f;
+#ifndef PWC_FFMA2
+#define PWC_FFMA2 1
+#endif
+        // Packed variant (stride2 = 1): the accumulators (p, d) and (p + 1, d - 1), p even, d = 1..8, both multiply the
+        // warped value w[p + d], which FFMA2 takes as its scalar (broadcast) operand, with the natural register pair
+        // (f[p], f[p + 1]); (even p, d = 0) and (odd p, d = 8) stay scalar.  32 FFMA2 + 8 FFMA instead of 72 FFMA per channel.
+        constexpr bool PACKED = PWC_FFMA2 && S2 == 1;
+        float2 ap[PX / 2][D - 1];
+#pragma unroll
+        for (int p = 0; p < PX / 2; ++p)
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) ap[p][d] = make_float2(0.0f, 0.0f);
 
         // A chunk's "consumed" signals are given one loop iteration late (or after the epilogue stores for
         // the last chunk of a tile): an mbarrier arrive issued right behind a still-pending LDS can overtake
@@ -769,6 +803,13 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const int p = jj - d * S2;
+                            if (PACKED) {
+                                if (p >= 0 && p < PX && (p & 1) == 0 && d >= 1)
+                                    ap[p >> 1][d - 1] = __ffma2_rn(make_float2(f[p], f[p + 1]), make_float2(w[jj], w[jj]), ap[p >> 1][d - 1]);
+                                if (p >= 0 && p < PX && (((p & 1) == 0 && d == 0) || ((p & 1) == 1 && d == D - 1)))
+                                    acc[p][d] = fmaf(f[p], w[jj], acc[p][d]);
+                                continue;
+                            }
                             if (p >= 0 && p < PX) acc[p][d] = fmaf(f[p], w[jj], acc[p][d]);
                         }
                     }
@@ -799,7 +840,12 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                 float v[PX];
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
-                    v[p] = acc[p][d] * inv_nelems;
+                    float a = acc[p][d];
+                    if (PACKED) {          // (even p, d >= 1) -> ap[p/2][d-1].x, (odd p, d <= 7) -> ap[p/2][d].y
+                        if ((p & 1) == 0 && d >= 1) a = ap[p >> 1][d - 1].x;
+                        if ((p & 1) == 1 && d <= D - 2) a = ap[p >> 1][d].y;
+                    }
+                    v[p] = a * inv_nelems;
                     if (act) v[p] = leaky(v[p], slope);
                 }
                 if (wide) {
