@@ -534,7 +534,11 @@ __device__ PWC_ROLE_ATTR void fwd_role_bilinear(const FwdArgs& A)
 #pragma unroll
             for (int c = 0; c < CK; ++c) {
                 const float* q = p + c * (WH * WW);
+#if defined(PWC_DEV_X) && PWC_DEV_X == 3
+                v[j][c] = tw[j].x;                             // (dev ablation) no loads at all
+#else
                 v[j][c] = fmaf(tw[j].w, q[WW + 1], fmaf(tw[j].z, q[WW], fmaf(tw[j].y, q[1], tw[j].x * q[0])));
+#endif
 #ifndef PWC_BGROUP
 #define PWC_BGROUP 2
 #endif
@@ -803,6 +807,9 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             const int p = jj - d * S2;
+#if defined(PWC_DEV_X) && PWC_DEV_X == 4
+                            if (d > 1) continue;                // (dev ablation) ~1/5 of the FMAs, all loads kept
+#endif
                             if (PACKED) {
                                 if (p >= 0 && p < PX && (p & 1) == 0 && d >= 1)
                                     ap[p >> 1][d - 1] = __ffma2_rn(make_float2(f[p], f[p + 1]), make_float2(w[jj], w[jj]), ap[p >> 1][d - 1]);
@@ -834,9 +841,11 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
         const int xs = tc.x0 + ls * PX;
         if (y < H && xs < W) {   // W % 4 == 0 and xs % 8 == 0: a strip is fully inside or ends on a multiple of 4
             const bool wide = out_32B_aligned && xs + PX <= W;     // the strip is one aligned 32-byte sector
+            // obs: output batch stride; the nine displacement planes of this thread are H * W floats apart
+            float* o = out + (size_t)tc.n * (size_t)obs + ((size_t)(wd * D) * H + y) * W + xs;
+            const size_t plane = (size_t)H * W;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                float* o = out + (size_t)tc.n * (size_t)obs + ((size_t)(wd * D + d) * H + y) * W + xs;   // obs: output batch stride
+            for (int d = 0; d < D; ++d, o += plane) {
                 float v[PX];
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {

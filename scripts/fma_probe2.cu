@@ -32,6 +32,13 @@ __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, float*
             } else if (MODE == 4) {   // FFMA2 8x4 outer product, scalar-broadcast a
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc2[i] = __ffma2_rn(make_float2(a[i >> 2], a[i >> 2]), make_float2(b[2 * (i & 3)], b[2 * (i & 3) + 1]), acc2[i]);
+            } else if (MODE == 6 || MODE == 7) {   // mixed: FFMA2 on one half of the accumulators, scalar FFMA on the other
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    acc2[(i & 7) * 2 + (i >> 3)] = __ffma2_rn(make_float2(a[i & 7], a[i & 7]), make_float2(b[2 * (i >> 3)], b[2 * (i >> 3) + 1]), acc2[(i & 7) * 2 + (i >> 3)]);
+#pragma unroll
+                    for (int u = 0; u < (MODE == 6 ? 2 : 1); ++u) acc[32 + 2 * i + u] = fmaf(a[0], b[0], acc[32 + 2 * i + u]);
+                }
             } else if (MODE == 5) {   // FFMA2 8x4, b outer (b pair reused), a scalar varies
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc2[(i & 7) * 4 + (i >> 3)] = __ffma2_rn(make_float2(a[i & 7], a[i & 7]), make_float2(b[2 * (i >> 3)], b[2 * (i >> 3) + 1]), acc2[(i & 7) * 4 + (i >> 3)]);
@@ -53,9 +60,11 @@ static void run(const char* name, int nthr, float* din, float* dout)
     cudaDeviceSynchronize();
     unsigned long long clk;
     cudaMemcpyFromSymbol(&clk, g_clk, sizeof(clk));
-    const double winst = (MODE >= 3 ? 128.0 : 256.0) * iters * nthr / 32 / 4;     // warp instructions per scheduler
+    const double fmas = MODE == 6 ? 256.0 : MODE == 7 ? 192.0 : 256.0;           // lane-FMAs per thread and iteration
+    const double insts = MODE == 6 ? 4 * 48.0 : MODE == 7 ? 4 * 32.0 : (MODE >= 3 ? 128.0 : 256.0);
+    const double winst = insts * iters * nthr / 32 / 4;     // warp instructions per scheduler
     printf("%-44s %4d thr: %.2f clk per warp instruction and scheduler, %.1f lane-FMA/clk/SM  %s\n", name, nthr,
-           clk / winst, 256.0 * iters * nthr / clk, cudaGetErrorString(cudaGetLastError()));
+           clk / winst, fmas * iters * nthr / clk, cudaGetErrorString(cudaGetLastError()));
 }
 int main()
 {
@@ -68,6 +77,8 @@ int main()
         run<3>("FFMA2 a,b fixed", nthr, din, dout);
         run<4>("FFMA2 8x4 outer, a outer", nthr, din, dout);
         run<5>("FFMA2 8x4 outer, b outer", nthr, din, dout);
+        run<6>("mixed: 16 FFMA2 + 32 FFMA per round", nthr, din, dout);
+        run<7>("mixed: 16 FFMA2 + 16 FFMA per round", nthr, din, dout);
     }
     return 0;
 }
