@@ -855,7 +855,10 @@ warpcorr_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_c
                         if ((p & 1) == 1 && d <= D - 2) a = ap[p >> 1][d].y;
                     }
                     v[p] = a * inv_nelems;
-                    if (act) v[p] = leaky(v[p], slope);
+                }
+                if (act) {      // one uniform branch per displacement, selects inside (not a branch per element)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) v[p] = v[p] < 0.0f ? v[p] * slope : v[p];
                 }
                 if (wide) {
                     st_global_v8(o, v);
