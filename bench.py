@@ -450,6 +450,28 @@ def run_native(args):
         torch.cuda.synchronize()
         fwd_ms = [a.elapsed_time(b) for a, b in pairs_ev]
         fwd_alone_ms = sum(fwd_ms) / len(fwd_ms)
+    # The same kernel with the flow SURVEY.md 8(d) calls typical -- 8x-downsampled noise, bilinearly upsampled, which is
+    # what model.py:78 hands to every level -- timed alone the same way; the headline roofline stays on the i.i.d. flow.
+    fwd_smooth_ms = None
+    try:
+        torch.manual_seed(1234 + rank)
+        smooth_sets = [make_set("smooth")["level2"] for _ in range(NSETS)]
+        torch.cuda._sleep(20_000_000)
+        pairs_sm = []
+        with torch.no_grad():
+            for i in range(33):
+                f1, f2, flow, _ = smooth_sets[i % NSETS]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                op(f1, f2, flow)
+                e1.record()
+                pairs_sm.append((e0, e1))
+        torch.cuda.synchronize()
+        sm = [a.elapsed_time(b) for a, b in pairs_sm[3:]]
+        fwd_smooth_ms = sum(sm) / len(sm)
+        del smooth_sets
+    except Exception:
+        fwd_smooth_ms = None
 
     # ---- timed region: device-resident inputs ----
     barrier()
@@ -659,6 +681,10 @@ def run_native(args):
                 "traffic_read_write": [tinfo.get("warpcorr_fwd_level2_dram_read_bytes"),
                                        tinfo.get("warpcorr_fwd_level2_dram_write_bytes")],
                 "binding_resource": lsu, "compute_floor": fma_floor, "peak_source": peak_src,
+                "typical_flow": (None if not fwd_smooth_ms else {
+                    "flow": "8x-downsampled N(0, 2^2) noise, bilinearly upsampled (SURVEY.md 8d 'typical'; what model.py:78 produces)",
+                    "avg_launch_ms_alone": fwd_smooth_ms,
+                    "frac": fwd_bytes(*SHAPES["level2"]) / fwd_smooth_ms / 1e6 / peak}),
                 "algorithmic_bytes_per_launch": fwd_bytes(B, C, H, W), "avg_launch_ms": fwd_l2_ms,
                 "timing": roofline_timing, "avg_launch_ms_alone": fwd_alone_ms,
                 "frac_of_nominal_8000": ach / 8000.0,
