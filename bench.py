@@ -780,7 +780,7 @@ def measure_network_legs(torch, dist, dev, rank, world, dump_kernels=None):
         for unused, cl in (("find", False), ("freeze", False), ("freeze", True)):
             ts = TrainStep(dev, batch=8, height=384, width=448, unused=unused, channels_last=cl)
             first = float(ts.step())
-            ms = timed(ts.step, iters=6, warm=2)
+            ms = timed(ts.step, iters=8, warm=5)      # (cuDNN picks / compiles kernels during the first steps: 2 warm-ups once gave 45 instead of 31 ms)
             row = {"ms_per_step": ms, "pairs_per_s": world * ts.batch / (ms * 1e-3),
                    "allreduce_bytes": ts.grad_bytes(), "bucket_cap_mb": ts.bucket_cap_mb,
                    "loss_first": first, "loss_last": float(ts.step())}
