@@ -17,10 +17,11 @@
 //                   shuffles), one tile ahead of the bilinear warps;
 //       B  5 warps: evaluate the bilinear warp out of the window into a ring of warped chunks
 //                   (taps live in registers for the whole tile, loads are batched for MLP);
-//       C  9 warps: warp wd owns displacement row tj = wd - 4, lane (lr, ls) owns an 8-pixel
-//                   strip and its 8x9 accumulators; correlate out of shared memory, then write
-//                   the cost volume.
-//     The stream of (tile, channel-chunk) work items is continuous across tiles.
+//       C  9 warps: a thread owns one (tile row, 8-pixel strip, displacement row) task and its 8x9
+//                   accumulators; correlate out of shared memory (packed FFMA2, quad-shared LDS.128
+//                   addresses for stride2 = 1), then write the cost volume.
+//     The stream of (tile, channel-chunk) work items is continuous across tiles.  For stride2 = 1 the
+//     last group of four warps hands 48 registers per thread to the first twelve (setmaxnreg).
 // Requires W % 4 == 0 and 16-byte aligned bases (TMA global strides are multiples of 16 bytes);
 // every TMA start coordinate along x is kept a multiple of 4 pixels (see TmaCfg::WW).
 #pragma once
