@@ -37,10 +37,11 @@ struct BwdSeqCfg {
     static constexpr uint32_t X_BYTES = X_ELEMS * 4;
     static constexpr int NTS = 6;                                       // tap ring slots
     static constexpr int SLOT_ELEMS = D * TH * TW;                      // 9 planes of one displacement row
-    static constexpr int CTRL_BYTES = 256;
+    static constexpr int CTRL_BYTES = 512;                              // tap slots start 512-byte aligned (64-byte TMA swizzle)
     static constexpr int GBOX_C = 27;
     static_assert(WP % 8 == 4, "pitch must be 4 mod 8 floats");
     static_assert((4 + 2 * NTS) * 8 <= CTRL_BYTES, "control block too small");
+    static_assert((CTRL_BYTES + 2 * X_BYTES) % 512 == 0 && (SLOT_ELEMS * 4) % 512 == 0, "swizzle atom alignment of the tap slots");
     static_assert(D % (NSTAGE / 32) == 0, "each staging warp owns the same displacement rows in every item");
     static constexpr size_t smem_bytes() { return CTRL_BYTES + 2 * (size_t)X_BYTES + (size_t)NTS * SLOT_ELEMS * 4; }
 };
@@ -48,6 +49,7 @@ struct BwdSeqCfg {
 template <int SIGN>
 __global__ void __launch_bounds__(BwdSeqCfg::NT, 1)
 corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ CUtensorMap tmTap, int tma_taps,
                     const float* __restrict__ gout, float* __restrict__ res,
                     int C, int H, int W, int tiles_x, int tiles_y, int nitems, int nsc, long long gbs)
 {
@@ -76,7 +78,8 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < NTS; ++i) {
-            mbar_init(&barTap[i], 64);          // per staging lane: one cp.async arrival + one plain arrival
+            // staging warps: per lane one cp.async arrival + one plain arrival; TMA taps: the expect_tx arrival
+            mbar_init(&barTap[i], (SIGN > 0 && tma_taps) ? 1 : 64);
             mbar_init(&barTapFree[i], NCONS);
         }
         fence_mbar_init();
@@ -86,6 +89,24 @@ corr_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (tid >= NCONS + 32) {
         // ================================ S: tap streaming ================================
         const int lane = tid & 31, sw = (tid - (NCONS + 32)) >> 5;      // sw owns rows dyi = sw, sw+3, sw+6
+        if (SIGN > 0 && tma_taps) {
+            // g1: one TMA request per displacement row ([9][16][16] box of the output gradient at the tile, zero
+            // fill outside the image, 64-byte swizzle = tap_slot()), NTS rows ahead of the consumers
+            if (sw != 0 || lane != 0) return;
+            prefetch_tmap(&tmTap);
+            int j = 0;
+            for (int it = 0; it < my_items; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const TileCoord tc = tile_coord(item / nsc, tiles_x, tiles_y, TH, TW);
+                for (int dyi = 0; dyi < D; ++dyi, ++j) {
+                    const int slot = j % NTS;
+                    if (j >= NTS) mbar_wait(&barTapFree[slot], ((j / NTS) - 1) & 1);
+                    mbar_expect_tx(&barTap[slot], Cfg::SLOT_ELEMS * 4);
+                    tma_load_4d(sTap + slot * Cfg::SLOT_ELEMS, &tmTap, &barTap[slot], tc.x0, tc.y0, dyi * D, tc.n);
+                }
+            }
+            return;
+        }
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const TileCoord tc = tile_coord(item / nsc, tiles_x, tiles_y, TH, TW);

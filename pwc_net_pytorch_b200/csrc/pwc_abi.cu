@@ -252,7 +252,7 @@ EncodeTiledFn encode_tiled_fn()
 // elements (image border, channel tail) are filled with zeros by the TMA unit.
 // batch_stride: floats between consecutive images (0 = dense, C*H*W); must be a multiple of 4 floats.
 bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int W, int bw, int bh, int bc,
-                   long long batch_stride = 0)
+                   long long batch_stride = 0, bool swizzle64 = false)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
@@ -263,7 +263,8 @@ bool make_nchw_map(CUtensorMap* map, const float* ptr, int B, int C, int H, int 
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
-                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -483,6 +484,12 @@ int launch_bwd_seq(const float* gout, long long gbs, const float* X, float* res,
     if (!make_nchw_map(&mG, gout, g.B, 81, g.H, g.W, SIGN > 0 ? Cfg::TW : Cfg::HWD, SIGN > 0 ? Cfg::TH : Cfg::HH,
                        Cfg::GBOX_C, gbs))
         return -1;
+    // g1: the taps of a displacement row are an unshifted [9][16][16] box of the output gradient -- TMA writes it
+    // straight into the tap ring (64-byte swizzle == tap_slot()); the other gradient reads them at x - dx, where a
+    // tiled load cannot start (16-byte rule), and keeps the staging warps
+    CUtensorMap mTap = mG;
+    int tma_taps = 0;
+    if (SIGN > 0 && make_nchw_map(&mTap, gout, g.B, 81, g.H, g.W, Cfg::TW, Cfg::TH, Cfg::D, gbs, true)) tma_taps = 1;
     auto kern = pwc::corr_bwd_seq_kernel<SIGN>;
     const size_t smem = Cfg::smem_bytes();
     static std::atomic<unsigned long long> configured_devs{0};   // one bit per device (the opt-in is per function and device)
@@ -499,7 +506,7 @@ int launch_bwd_seq(const float* gout, long long gbs, const float* X, float* res,
     if (nitems > 0x3fffffffLL) return fail("grid too large");
     const int sms = sm_count_of_current_device();
     const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
-    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)nitems, nsc, gbs);
+    kern<<<grid, Cfg::NT, smem, st>>>(mX, mG, mTap, tma_taps, gout, res, g.C, g.H, g.W, tiles_x, tiles_y, (int)nitems, nsc, gbs);
     return check_launch("corr_bwd_seq_kernel");
 }
 
