@@ -454,6 +454,8 @@ def run_native(args):
     # what model.py:78 hands to every level -- timed alone the same way; the headline roofline stays on the i.i.d. flow.
     fwd_smooth_ms = None
     try:
+        if graphs is None:
+            raise RuntimeError("eager mode: keep the launch list of the timed step clean")
         torch.manual_seed(1234 + rank)
         smooth_sets = [make_set("smooth")["level2"] for _ in range(NSETS)]
         torch.cuda._sleep(20_000_000)
